@@ -1,0 +1,134 @@
+"""ctypes binding of ``include/basicrta_b200.h`` (the C-ABI drop-in boundary).
+
+This is the stub a basicrta maintainer would add.  There is no CPU
+fallback: if ``libbrta_gibbs.so`` is missing or the device is not a CUDA GPU the calls
+raise :class:`BrtaError`.
+"""
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libbrta_gibbs.so')
+SRC = os.path.join(HERE, 'csrc', 'brta_gibbs.cu')
+INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
+
+ABI_VERSION = 1
+THREADS = 256
+MAX_NCOMP = 32
+TICK_LIMIT = 1 << 23
+EXCH_STRIDE = 1280
+
+FLAG_EXACT = 1
+FLAG_INJECT_COEF = 2
+FLAG_INJECT_U = 4
+FLAG_TRACE = 8
+
+STATUS_OK = 0
+STATUS_NONFINITE = 1
+
+
+class BrtaError(RuntimeError):
+    pass
+
+
+class Caps(C.Structure):
+    _fields_ = [('abi_version', C.c_int32), ('cc_major', C.c_int32), ('cc_minor', C.c_int32),
+                ('sm_count', C.c_int32), ('max_smem_per_cta', C.c_int32),
+                ('threads_per_cta', C.c_int32), ('max_ncomp', C.c_int32),
+                ('exch_stride', C.c_int32)]
+
+
+class LaunchInfo(C.Structure):
+    _fields_ = [('ctas_per_sm', C.c_int32), ('regs_per_thread', C.c_int32),
+                ('static_smem', C.c_int32), ('kernel_ncomp', C.c_int32)]
+
+
+class Task(C.Structure):
+    _fields_ = [('chain', C.c_int32), ('team_size', C.c_int32), ('team_rank', C.c_int32),
+                ('quad_begin', C.c_int32), ('quad_count', C.c_int32), ('order', C.c_int32)]
+
+
+class Batch(C.Structure):
+    _fields_ = [
+        ('n_chains', C.c_int32), ('ncomp', C.c_int32), ('niter', C.c_int32), ('thin', C.c_int32),
+        ('tick_bytes', C.c_int32), ('flags', C.c_uint32), ('seed', C.c_uint64),
+        ('ticks', C.c_void_p), ('tick_offset', C.c_void_p), ('n_data', C.c_void_p),
+        ('chain_id', C.c_void_p), ('ts', C.c_void_p), ('whyper', C.c_void_p),
+        ('rhyper', C.c_void_p), ('init_c', C.c_void_p), ('init_a', C.c_void_p),
+        ('mcweights', C.c_void_p), ('mcrates', C.c_void_p), ('indicator', C.c_void_p),
+        ('ind_offset', C.c_void_p), ('ind_stride', C.c_void_p), ('status', C.c_void_p),
+        ('inj_c', C.c_void_p), ('inj_a', C.c_void_p), ('inj_u', C.c_void_p),
+        ('inj_u_offset', C.c_void_p), ('trace_nk', C.c_void_p), ('trace_tk', C.c_void_p),
+        ('tasks', C.c_void_p), ('cta_task_begin', C.c_void_p), ('grid_ctas', C.c_int32),
+        ('slice_cap_quads', C.c_int32), ('exchange', C.c_void_p),
+    ]
+
+
+EXPORTS = ('brta_abi_version', 'brta_last_error', 'brta_query', 'brta_gibbs_launch_info',
+           'brta_gibbs_run_batch', 'brta_philox_fill')
+
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+              '-shared', '-Xcompiler', '-fPIC']
+
+
+def build(force=False, verbose=False):
+    """Compile ``csrc/brta_gibbs.cu`` for sm_100a into ``libbrta_gibbs.so`` (in-tree)."""
+    srcs = [SRC] + [os.path.join(HERE, 'csrc', f) for f in ('brta_math.cuh', 'brta_rng.cuh')] + \
+           [os.path.join(INCLUDE, 'basicrta_b200.h')]
+    if (not force and os.path.exists(LIB_PATH) and
+            all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
+        return LIB_PATH
+    cmd = ['nvcc'] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH, SRC]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise BrtaError('nvcc failed:\n' + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BrtaError(f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; '
+                        f'g.build()"` (nvcc, sm_100a). basicrta_b200 has no CPU fallback.')
+    lib = C.CDLL(LIB_PATH)
+    lib.brta_abi_version.restype = C.c_int
+    lib.brta_last_error.restype = C.c_char_p
+    lib.brta_query.argtypes = [C.c_int, C.POINTER(Caps)]
+    lib.brta_gibbs_launch_info.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_int, C.POINTER(LaunchInfo)]
+    lib.brta_gibbs_run_batch.argtypes = [C.POINTER(Batch), C.c_void_p]
+    lib.brta_philox_fill.argtypes = [C.c_void_p, C.c_int64, C.c_uint32, C.c_uint32, C.c_uint32,
+                                     C.c_uint32, C.c_uint64, C.c_void_p]
+    for name in EXPORTS:
+        getattr(lib, name)
+    if lib.brta_abi_version() != ABI_VERSION:
+        raise BrtaError('libbrta_gibbs.so ABI version mismatch; rebuild')
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().brta_last_error().decode()
+        raise BrtaError(f'{what} failed (rc={rc}): {msg}')
+
+
+def query(device):
+    caps = Caps()
+    check(load().brta_query(int(device), C.byref(caps)), 'brta_query')
+    return caps
+
+
+def launch_info(device, ncomp, flags, slice_cap_quads):
+    info = LaunchInfo()
+    check(load().brta_gibbs_launch_info(int(device), int(ncomp), int(flags), int(slice_cap_quads),
+                                        C.byref(info)), 'brta_gibbs_launch_info')
+    return info

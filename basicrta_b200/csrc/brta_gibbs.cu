@@ -1,0 +1,521 @@
+// B200 (sm_100a) Gibbs sweep for basicrta's exponential-mixture residence-time model.
+//
+// Replaces the loop body of basicrta/gibbs.py:191-217 (reference: NumPy, one process per
+// residue) by ONE persistent cooperative launch per batch of residues:
+//
+//   * a chain (residue) is owned by a *team* of CTAs chosen by the host schedule
+//     (basicrta_b200/plan.py); each CTA keeps its slice of the residence times in shared
+//     memory as float ticks for the whole run (times are integer multiples of ts,
+//     basicrta/contacts.py:222-229);
+//   * per iteration every thread handles "quads" of 4 data: one Philox4x32-10 call gives
+//     the 4 uniforms, the K logits  c_k - a_k*tick  live in registers, max-subtracted
+//     exp2 (MUFU.EX2), sequential cumulative sum, inverse-CDF label
+//     (gibbs.py:196-200);
+//   * sufficient statistics (n_k, sum of ticks) are exact integers (gibbs.py:203-207):
+//     shared-memory atomics for every label except the currently dominant one, whose
+//     statistics follow by subtraction from the slice totals;
+//   * team members add their partials into the chain's exchange buffer in L2
+//     (red.global.add) and rendezvous on a monotonic arrive counter; every member then
+//     draws the same Dirichlet / Gamma update (gibbs.py:210-211) from the same Philox
+//     key with one warp (lane k = component k), so no broadcast is needed;
+//   * every `thin`-th iteration the labels (4 per 32-bit store) and, from team rank 0,
+//     the post-update weights/rates are written (gibbs.py:214-217).
+//
+// No tensor cores: nothing here is a contraction.  The roofline is the MUFU (XU) pipe:
+// one ex2 per (datum, component) pair.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/basicrta_b200.h"
+#include "brta_math.cuh"
+#include "brta_rng.cuh"
+
+namespace brta {
+
+constexpr int THREADS = BRTA_THREADS;
+constexpr int WARPS = THREADS / 32;
+
+// exchange workspace of one chain (BRTA_EXCH_STRIDE bytes):
+//   sum[3][32] u64 @ 0, cnt[3][32] u32 @ 768, arrive u32 @ 1152
+constexpr int EXCH_SUM_OFF = 0;
+constexpr int EXCH_CNT_OFF = 768;
+constexpr int EXCH_ARRIVE_OFF = 1152;
+static_assert(EXCH_ARRIVE_OFF + 4 <= BRTA_EXCH_STRIDE, "exchange layout");
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Branch-free binary search in a sorted register array: the number of k with cum[k] <= thr.
+// cum is non-decreasing (sums of non-negative terms), so this equals the linear count the
+// oracle performs.  Level l compares against one pivot chosen from 2^(l-1) candidates by
+// the earlier predicates; the latest predicate drives the outermost select so only one
+// FSEL sits behind each FSETP.  K compares + K adds become ~log2(K) compares + K selects.
+template <int K, int P, int NB, int OFF, int STR>
+__device__ __forceinline__ float pivot_mux(const float (&cum)[K], const bool (&p)[5])
+{
+    if constexpr (NB == 0) {
+        if constexpr (OFF < P) return cum[OFF]; else return INFINITY;
+    } else {
+        const float hi = pivot_mux<K, P, NB - 1, OFF + STR, 2 * STR>(cum, p);
+        const float lo = pivot_mux<K, P, NB - 1, OFF, 2 * STR>(cum, p);
+        return p[NB - 1] ? hi : lo;
+    }
+}
+
+// level LVL of LEVELS: candidate j (bits p[0..LVL-2], p[0] most significant) sits at
+// index (2j+1) * 2^(LEVELS-LVL) - 1.
+template <int K, int P, int LEVELS, int LVL>
+__device__ __forceinline__ void search_level(const float (&cum)[K], float thr, bool (&p)[5], int& c)
+{
+    if constexpr (LVL <= LEVELS) {
+        const float pv = pivot_mux<K, P, LVL - 1, (1 << (LEVELS - LVL)) - 1, 1 << (LEVELS - LVL + 1)>(cum, p);
+        p[LVL - 1] = pv <= thr;
+        c += p[LVL - 1] ? (1 << (LEVELS - LVL)) : 0;
+        search_level<K, P, LEVELS, LVL + 1>(cum, thr, p, c);
+    }
+}
+
+template <int K>
+__device__ __forceinline__ int count_le(const float (&cum)[K], float thr)
+{
+    // tree over the first P = 2^LEVELS - 1 (padded with +inf) entries; a power-of-two K
+    // keeps its last entry out of the tree and tests it directly.
+    constexpr bool POW2 = (K & (K - 1)) == 0;
+    constexpr int P = POW2 ? K - 1 : K;
+    constexpr int LEVELS = (P >= 16) ? 5 : (P >= 8) ? 4 : (P >= 4) ? 3 : (P >= 2) ? 2 : (P >= 1) ? 1 : 0;
+    bool p[5] = {false, false, false, false, false};
+    int c = 0;
+    search_level<K, P, LEVELS, 1>(cum, thr, p, c);
+    if constexpr (POW2) c += (cum[K - 1] <= thr) ? 1 : 0;
+    return c;
+}
+
+// Labels of D data at once.  l[d][k] holds the logit, then the running cumulative sum.
+template <int K, int D, bool EXACT>
+__device__ __forceinline__ void draw_labels(const float (&tick)[D], const float (&u)[D],
+                                            const float2* __restrict__ s_coef, int kmax,
+                                            int (&lab)[D], bool& bad)
+{
+    float l[D][K];
+    float m[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) m[d] = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const float2 ca = s_coef[k];                       // broadcast LDS
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            l[d][k] = EXACT ? __fsub_rn(ca.x, __fmul_rn(ca.y, tick[d]))
+                            : fmaf(-ca.y, tick[d], ca.x);
+            m[d] = fmaxf(m[d], l[d][k]);
+        }
+    }
+    float cum[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) cum[d] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            if (EXACT) {
+                cum[d] = __fadd_rn(cum[d], soft_exp2(__fsub_rn(l[d][k], m[d])));
+            } else {
+                cum[d] += fast_exp2(l[d][k] - m[d]);
+            }
+            l[d][k] = cum[d];
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const float thr = EXACT ? __fmul_rn(u[d], cum[d]) : u[d] * cum[d];
+        lab[d] = min(count_le<K>(l[d], thr), kmax);
+        bad |= !(cum[d] > 0.5f);                           // the max term contributes 1; catches NaN
+    }
+}
+
+template <int K, bool EXACT>
+__global__ void __launch_bounds__(THREADS)
+gibbs_sweep_kernel(const brta_batch b)
+{
+    constexpr int D = (K <= 16) ? 4 : 2;                   // data in flight per thread
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* s_tick4 = reinterpret_cast<float4*>(smem_raw);
+
+    __shared__ __align__(16) float2 s_coef[32];            // {coef_c, coef_a}
+    __shared__ unsigned s_cnt[32];
+    __shared__ unsigned s_sum[32];                         // per-iteration slice sums fit 32 bits (host-checked)
+    __shared__ unsigned long long s_red_t[WARPS];
+    __shared__ unsigned s_red_n[WARPS];
+    __shared__ int s_dom;
+    __shared__ unsigned s_bad;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const uint32_t key0 = (uint32_t)b.seed;
+    const uint32_t key1 = (uint32_t)(b.seed >> 32);
+    const int kreal = b.ncomp;
+    const int niter = b.niter;
+    const int thin = b.thin;
+    const int rows = (niter + 1) / thin;
+    const bool inject_coef = (b.flags & BRTA_FLAG_INJECT_COEF) != 0;
+    const bool inject_u = (b.flags & BRTA_FLAG_INJECT_U) != 0;
+    const bool trace = (b.flags & BRTA_FLAG_TRACE) != 0;
+
+    const int task_end = b.cta_task_begin[blockIdx.x + 1];
+    for (int ti = b.cta_task_begin[blockIdx.x]; ti < task_end; ++ti) {
+        const brta_task task = b.tasks[ti];
+        const int r = task.chain;
+        const int n_data = b.n_data[r];
+        const int nq = task.quad_count;
+        const int qb = task.quad_begin;
+        const uint32_t chain_id = b.chain_id[r];
+        const float ts = b.ts[r];
+        const int64_t tick_off = b.tick_offset[r];
+        const int ind_stride = b.ind_stride[r];
+        uint8_t* const ind_base = b.indicator + b.ind_offset[r];
+        const float* const inj_u_base = inject_u ? b.inj_u + b.inj_u_offset[r] : nullptr;
+        const size_t u_pitch = (size_t)((n_data + 3) / 4) * 4;
+
+        // ---- stage the slice: integer ticks -> float32 in shared memory -----------------
+        unsigned my_n = 0;
+        unsigned long long my_t = 0;
+        for (int q = tid; q < nq; q += THREADS) {
+            const int i0 = (qb + q) * 4;
+            unsigned t0, t1, t2, t3;
+            if (b.tick_bytes == 2) {
+                const ushort4 raw = reinterpret_cast<const ushort4*>(
+                    static_cast<const uint16_t*>(b.ticks) + tick_off)[qb + q];
+                t0 = raw.x; t1 = raw.y; t2 = raw.z; t3 = raw.w;
+            } else {
+                const uint4 raw = reinterpret_cast<const uint4*>(
+                    static_cast<const uint32_t*>(b.ticks) + tick_off)[qb + q];
+                t0 = raw.x; t1 = raw.y; t2 = raw.z; t3 = raw.w;
+            }
+            if (i0 + 0 >= n_data) t0 = 0;
+            if (i0 + 1 >= n_data) t1 = 0;
+            if (i0 + 2 >= n_data) t2 = 0;
+            if (i0 + 3 >= n_data) t3 = 0;
+            my_n += (unsigned)min(4, max(0, n_data - i0));
+            my_t += (unsigned long long)t0 + t1 + t2 + t3;
+            s_tick4[q] = make_float4((float)t0, (float)t1, (float)t2, (float)t3);
+        }
+        my_n = __reduce_add_sync(FULL, my_n);
+        my_t = warp_sum_u64(my_t);
+        if (lane == 0) { s_red_n[warp] = my_n; s_red_t[warp] = my_t; }
+        if (tid < 32) {
+            float2 ca = make_float2(-INFINITY, 0.0f);
+            if (tid < kreal && !inject_coef)
+                ca = make_float2(b.init_c[(size_t)r * kreal + tid], b.init_a[(size_t)r * kreal + tid]);
+            s_coef[tid] = ca;
+            s_cnt[tid] = 0;
+            s_sum[tid] = 0;
+        }
+        if (tid == 0) { s_dom = 0; s_bad = 0; }
+        __syncthreads();
+
+        // slice totals and per-component priors live in warp 0's registers
+        unsigned slice_n = 0;
+        unsigned long long slice_t = 0;
+        float wh = 0.0f, rh_a = 1.0f, rh_b = 1.0f;
+        if (warp == 0) {
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) { slice_n += s_red_n[w]; slice_t += s_red_t[w]; }
+            if (lane < kreal) {
+                wh = b.whyper[(size_t)r * kreal + lane];
+                rh_a = b.rhyper[((size_t)r * kreal + lane) * 2 + 0];
+                rh_b = b.rhyper[((size_t)r * kreal + lane) * 2 + 1];
+            }
+        }
+        unsigned char* const exch = static_cast<unsigned char*>(b.exchange) + (size_t)r * BRTA_EXCH_STRIDE;
+        unsigned long long* const ex_sum = reinterpret_cast<unsigned long long*>(exch + EXCH_SUM_OFF);
+        unsigned* const ex_cnt = reinterpret_cast<unsigned*>(exch + EXCH_CNT_OFF);
+        unsigned* const ex_arrive = reinterpret_cast<unsigned*>(exch + EXCH_ARRIVE_OFF);
+
+        bool bad = false;
+        for (int j = 1; j <= niter; ++j) {
+            if (inject_coef) {
+                if (tid < kreal) {
+                    const size_t o = ((size_t)r * niter + (j - 1)) * kreal + tid;
+                    s_coef[tid] = make_float2(b.inj_c[o], b.inj_a[o]);
+                }
+                __syncthreads();
+            }
+            const bool save = (j % thin == 0) && (j / thin - 1 < rows);
+            uint8_t* const ind_row = ind_base + (size_t)(save ? j / thin - 1 : 0) * ind_stride;
+            const float4* const u_row = inject_u
+                ? reinterpret_cast<const float4*>(inj_u_base + (size_t)(j - 1) * u_pitch) : nullptr;
+            const int dom = s_dom;
+
+            // ---- indicator draws + sufficient statistics (gibbs.py:196-207) -------------
+            for (int q = tid; q < nq; q += THREADS) {
+                const float4 tk = s_tick4[q];
+                const int i0 = (qb + q) * 4;
+                float4 uu;
+                if (inject_u) {
+                    uu = u_row[qb + q];
+                } else {
+                    const Words4 w = philox4x32_10((uint32_t)(qb + q), (uint32_t)j, chain_id, 0u, key0, key1);
+                    uu = make_float4(word_to_unit(w.x), word_to_unit(w.y), word_to_unit(w.z), word_to_unit(w.w));
+                }
+                const float tks[4] = {tk.x, tk.y, tk.z, tk.w};
+                const float us[4] = {uu.x, uu.y, uu.z, uu.w};
+                int labs[4];
+#pragma unroll
+                for (int h = 0; h < 4; h += D) {
+                    float td[D], ud[D];
+                    int ld[D];
+#pragma unroll
+                    for (int d = 0; d < D; ++d) { td[d] = tks[h + d]; ud[d] = us[h + d]; }
+                    draw_labels<K, D, EXACT>(td, ud, s_coef, kreal - 1, ld, bad);
+#pragma unroll
+                    for (int d = 0; d < D; ++d) labs[h + d] = ld[d];
+                }
+#pragma unroll
+                for (int d = 0; d < 4; ++d) {
+                    if (labs[d] != dom && i0 + d < n_data) {
+                        atomicAdd(&s_cnt[labs[d]], 1u);
+                        atomicAdd(&s_sum[labs[d]], __float2uint_rn(tks[d]));
+                    }
+                }
+                if (save) {                                // 1 iteration in `thin`: byte stores, dense [S,N]
+#pragma unroll
+                    for (int d = 0; d < 4; ++d)
+                        if (i0 + d < n_data) ind_row[i0 + d] = (uint8_t)labs[d];
+                }
+            }
+            __syncthreads();
+
+            // ---- team exchange + posterior update (gibbs.py:210-211): warp 0 ------------
+            if (warp == 0) {
+                unsigned cnt = s_cnt[lane];
+                unsigned long long sum = (unsigned long long)s_sum[lane];
+                s_cnt[lane] = 0;
+                s_sum[lane] = 0;
+                {   // the dominant label was not counted: recover it from the slice totals
+                    const unsigned oc = __reduce_add_sync(FULL, cnt);
+                    const unsigned long long os = warp_sum_u64(sum);
+                    if (lane == dom) { cnt = slice_n - oc; sum = slice_t - os; }
+                }
+                if (task.team_size > 1) {
+                    const int buf = j % 3;
+                    if (cnt != 0u) {
+                        atomicAdd(&ex_cnt[buf * 32 + lane], cnt);
+                        atomicAdd(&ex_sum[buf * 32 + lane], sum);
+                    }
+                    __syncwarp();
+                    if (lane == 0) {
+                        __threadfence();
+                        atomicAdd(ex_arrive, 1u);
+                    }
+                    const unsigned target = (unsigned)task.team_size * (unsigned)j;
+                    while (ld_acquire_u32(ex_arrive) < target) __nanosleep(40);
+                    cnt = ld_relaxed_u32(&ex_cnt[buf * 32 + lane]);
+                    sum = ld_relaxed_u64(&ex_sum[buf * 32 + lane]);
+                    if (task.team_rank == 0) {             // recycle the buffer last read in j-1
+                        const int old = (j + 2) % 3;
+                        ex_cnt[old * 32 + lane] = 0u;
+                        ex_sum[old * 32 + lane] = 0ull;
+                    }
+                }
+                if (trace && task.team_rank == 0 && lane < kreal) {
+                    const size_t o = ((size_t)r * niter + (j - 1)) * kreal + lane;
+                    b.trace_nk[o] = (int64_t)cnt;
+                    b.trace_tk[o] = (int64_t)sum;
+                }
+                // next iteration skips the most populated label in the atomics
+                {
+                    const unsigned keyv = (lane < kreal) ? ((cnt << 5) | (unsigned)(31 - lane)) : 0u;
+                    const unsigned best = __reduce_max_sync(FULL, keyv);
+                    if (lane == 0) s_dom = 31 - (int)(best & 31u);
+                }
+                if (!inject_coef) {
+                    const bool live = lane < kreal;
+                    const float fcnt = (float)cnt;
+                    float lgw = -INFINITY, lgr = 0.0f;
+                    if (live) {
+                        lgw = log_gamma_draw(wh + fcnt, (uint32_t)j, chain_id, 1u + 4u * lane, key0, key1);
+                        lgr = log_gamma_draw(rh_a + fcnt, (uint32_t)j, chain_id, 2u + 4u * lane, key0, key1)
+                              - logf(fmaf((float)sum, ts, rh_b));
+                    }
+                    const float mx = warp_max(lgw);
+                    const float tot = warp_sum(live ? expf(lgw - mx) : 0.0f);
+                    const float lnw = lgw - mx - logf(tot);
+                    const float rate = expf(lgr);
+                    if (live) s_coef[lane] = make_float2((lnw + lgr) * LOG2E, rate * (ts * LOG2E));
+                    if (save && task.team_rank == 0 && live) {
+                        const size_t o = ((size_t)r * rows + (j / thin - 1)) * kreal + lane;
+                        b.mcweights[o] = exp((double)lnw);
+                        b.mcrates[o] = (double)rate;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (bad) atomicOr(&s_bad, 1u);
+        __syncthreads();
+        if (tid == 0 && s_bad) atomicOr(reinterpret_cast<unsigned*>(&b.status[r]), (unsigned)BRTA_STATUS_NONFINITE);
+        __syncthreads();
+    }
+}
+
+__global__ void philox_fill_kernel(uint32_t* out, int64_t n, uint32_t x0, uint32_t c1, uint32_t c2,
+                                   uint32_t c3, uint32_t k0, uint32_t k1)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Words4 w = philox4x32_10(x0 + (uint32_t)i, c1, c2, c3, k0, k1);
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(w.x, w.y, w.z, w.w);
+}
+
+// ---- host side ----------------------------------------------------------------------
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, const char* detail = "")
+{
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* where)
+{
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return (int)e;
+}
+
+typedef void (*kernel_fn)(const brta_batch);
+
+struct Variant { int k; kernel_fn fast; kernel_fn exact; };
+
+#define BRTA_VARIANT(KK) {KK, gibbs_sweep_kernel<KK, false>, gibbs_sweep_kernel<KK, true>}
+const Variant g_variants[] = {
+    BRTA_VARIANT(2),  BRTA_VARIANT(3),  BRTA_VARIANT(4),  BRTA_VARIANT(5),  BRTA_VARIANT(6),
+    BRTA_VARIANT(8),  BRTA_VARIANT(10), BRTA_VARIANT(12), BRTA_VARIANT(15), BRTA_VARIANT(16),
+    BRTA_VARIANT(20), BRTA_VARIANT(24), BRTA_VARIANT(30), BRTA_VARIANT(32),
+};
+
+const Variant* pick_variant(int ncomp)
+{
+    for (const Variant& v : g_variants)
+        if (v.k >= ncomp) return &v;
+    return nullptr;
+}
+
+}  // namespace brta
+
+extern "C" {
+
+int brta_abi_version(void) { return BRTA_ABI_VERSION; }
+
+const char* brta_last_error(void) { return brta::g_err; }
+
+int brta_query(int device, brta_caps* caps)
+{
+    if (!caps) return brta::fail(BRTA_E_NULL, "brta_query: caps is NULL");
+    cudaDeviceProp p;
+    cudaError_t e = cudaGetDeviceProperties(&p, device);
+    if (e != cudaSuccess) return brta::cuda_fail(e, "cudaGetDeviceProperties");
+    caps->abi_version = BRTA_ABI_VERSION;
+    caps->cc_major = p.major;
+    caps->cc_minor = p.minor;
+    caps->sm_count = p.multiProcessorCount;
+    caps->max_smem_per_cta = (int32_t)p.sharedMemPerBlockOptin;
+    caps->threads_per_cta = BRTA_THREADS;
+    caps->max_ncomp = BRTA_MAX_NCOMP;
+    caps->exch_stride = BRTA_EXCH_STRIDE;
+    return 0;
+}
+
+int brta_gibbs_launch_info(int device, int ncomp, uint32_t flags, int slice_cap_quads,
+                           brta_launch_info* info)
+{
+    if (!info) return brta::fail(BRTA_E_NULL, "brta_gibbs_launch_info: info is NULL");
+    const brta::Variant* v = brta::pick_variant(ncomp);
+    if (ncomp < 1 || !v) return brta::fail(BRTA_E_NCOMP, "ncomp must be in 1..32");
+    brta::kernel_fn fn = (flags & BRTA_FLAG_EXACT) ? v->exact : v->fast;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return brta::cuda_fail(e, "cudaSetDevice");
+    const size_t smem = (size_t)slice_cap_quads * 16;
+    e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return brta::cuda_fail(e, "cudaFuncSetAttribute(smem)");
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, (const void*)fn);
+    if (e != cudaSuccess) return brta::cuda_fail(e, "cudaFuncGetAttributes");
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)fn, BRTA_THREADS, smem);
+    if (e != cudaSuccess) return brta::cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    info->ctas_per_sm = per_sm;
+    info->regs_per_thread = fa.numRegs;
+    info->static_smem = (int32_t)fa.sharedSizeBytes;
+    info->kernel_ncomp = v->k;
+    return 0;
+}
+
+int brta_gibbs_run_batch(const brta_batch* batch, void* stream)
+{
+    if (!batch) return brta::fail(BRTA_E_NULL, "brta_gibbs_run_batch: batch is NULL");
+    const brta_batch& b = *batch;
+    const brta::Variant* v = brta::pick_variant(b.ncomp);
+    if (b.ncomp < 1 || !v) return brta::fail(BRTA_E_NCOMP, "ncomp must be in 1..32");
+    if (b.n_chains < 1 || b.niter < 1 || b.thin < 1 || b.grid_ctas < 1 || b.slice_cap_quads < 1)
+        return brta::fail(BRTA_E_RANGE, "n_chains, niter, thin, grid_ctas, slice_cap_quads must be >= 1");
+    if (b.tick_bytes != 2 && b.tick_bytes != 4)
+        return brta::fail(BRTA_E_RANGE, "tick_bytes must be 2 or 4");
+    if (!b.ticks || !b.tick_offset || !b.n_data || !b.chain_id || !b.ts || !b.whyper || !b.rhyper ||
+        !b.indicator || !b.ind_offset || !b.ind_stride || !b.status || !b.tasks ||
+        !b.cta_task_begin || !b.exchange)
+        return brta::fail(BRTA_E_NULL, "brta_gibbs_run_batch: a required pointer is NULL");
+    if (b.flags & BRTA_FLAG_INJECT_COEF) {
+        if (!b.inj_c || !b.inj_a) return brta::fail(BRTA_E_NULL, "INJECT_COEF needs inj_c and inj_a");
+    } else if (!b.init_c || !b.init_a || !b.mcweights || !b.mcrates) {
+        return brta::fail(BRTA_E_NULL, "init_c, init_a, mcweights, mcrates are required");
+    }
+    if ((b.flags & BRTA_FLAG_INJECT_U) && (!b.inj_u || !b.inj_u_offset))
+        return brta::fail(BRTA_E_NULL, "INJECT_U needs inj_u and inj_u_offset");
+    if ((b.flags & BRTA_FLAG_TRACE) && (!b.trace_nk || !b.trace_tk))
+        return brta::fail(BRTA_E_NULL, "TRACE needs trace_nk and trace_tk");
+
+    brta::kernel_fn fn = (b.flags & BRTA_FLAG_EXACT) ? v->exact : v->fast;
+    const size_t smem = (size_t)b.slice_cap_quads * 16;
+    cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return brta::cuda_fail(e, "cudaFuncSetAttribute(smem)");
+    void* args[] = {(void*)batch};
+    e = cudaLaunchCooperativeKernel((const void*)fn, dim3((unsigned)b.grid_ctas), dim3(BRTA_THREADS), args,
+                                    smem, (cudaStream_t)stream);
+    if (e != cudaSuccess) return brta::cuda_fail(e, "cudaLaunchCooperativeKernel");
+    return 0;
+}
+
+int brta_philox_fill(uint32_t* out_dev, int64_t n, uint32_t x0, uint32_t c1, uint32_t c2, uint32_t c3,
+                     uint64_t seed, void* stream)
+{
+    if (!out_dev) return brta::fail(BRTA_E_NULL, "brta_philox_fill: out is NULL");
+    if (n <= 0) return 0;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    brta::philox_fill_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
+        out_dev, n, x0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return brta::cuda_fail(e, "philox_fill_kernel");
+    return 0;
+}
+
+}  // extern "C"

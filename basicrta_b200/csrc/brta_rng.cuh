@@ -1,0 +1,61 @@
+// Philox4x32-10 counter-based generator (Salmon et al., SC'11), device + host.
+//
+// The reference draws from an unseeded NumPy PCG64 (basicrta/gibbs.py:17); a device
+// sampler needs a stream addressable by (seed, chain, iteration, datum) so that the
+// result does not depend on how a chain is split over CTAs or GPUs.  Host mirror:
+// oracle/philox.py (pinned by the Random123 known-answer vectors).
+//
+//   key     = (seed & 0xffffffff, seed >> 32)
+//   counter = (x, iteration, chain_id, purpose)
+//   purpose 0        indicator uniforms, x = datum >> 2, datum i uses word (i & 3)
+//   purpose 1 + 4k   Dirichlet gamma of component k, x = rejection trial
+//   purpose 2 + 4k   rate gamma of component k,      x = rejection trial
+#pragma once
+#include <stdint.h>
+
+namespace brta {
+
+struct Words4 { uint32_t x, y, z, w; };
+
+constexpr uint32_t PHILOX_M0 = 0xD2511F53u;
+constexpr uint32_t PHILOX_M1 = 0xCD9E8D57u;
+constexpr uint32_t PHILOX_W0 = 0x9E3779B9u;
+constexpr uint32_t PHILOX_W1 = 0xBB67AE85u;
+
+__host__ __device__ __forceinline__ Words4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                         uint32_t c3, uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int round = 0; round < 10; ++round) {
+        const uint64_t p0 = (uint64_t)PHILOX_M0 * c0;     // IMAD.WIDE.U32
+        const uint64_t p1 = (uint64_t)PHILOX_M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += PHILOX_W0;
+        k1 += PHILOX_W1;
+    }
+    return Words4{c0, c1, c2, c3};
+}
+
+// uint32 -> float32 in [0,1): the top 23 bits become the mantissa of a float in [1,2).
+// Exact, no I2F (keeps the XU pipe for MUFU.EX2).  Mirror: oracle/philox.py word_to_uniform.
+__device__ __forceinline__ float word_to_unit(uint32_t w)
+{
+    return __uint_as_float(0x3f800000u | (w >> 9)) - 1.0f;
+}
+
+// (0,1] and (0,1) variants for the posterior draws (24 bits).
+__device__ __forceinline__ float word_to_unit_open_low(uint32_t w)   // (0, 1]
+{
+    return (float)((w >> 8) + 1u) * 5.9604644775390625e-08f;
+}
+__device__ __forceinline__ float word_to_unit_open(uint32_t w)       // (0, 1)
+{
+    return ((float)(w >> 8) + 0.5f) * 5.9604644775390625e-08f;
+}
+
+}  // namespace brta

@@ -1,0 +1,316 @@
+"""Host side of the batch sampler: packs chains into the device layout, builds the
+schedule, calls the C ABI (``brta_gibbs_run_batch``) and brings the results back.
+
+PyTorch is used for device memory, pinned host memory and streams only; the compute is
+the hand-written kernel in ``csrc/brta_gibbs.cu``.  There is no CPU path: every entry
+point raises if CUDA or the built library is unavailable.
+
+Layout in HBM (one batch = the residues one GPU runs in one launch):
+
+=================  ==========================  ==========================================
+buffer             shape / dtype               notes
+=================  ==========================  ==========================================
+ticks              uint16 or uint32 [sum N8]   times as multiples of ts, chain-concatenated,
+                                               each chain padded to 8 elements (16 B)
+per-chain scalars  n_data, tick_offset, ...    [R]
+whyper, rhyper     float32 [R,K], [R,K,2]      basicrta/gibbs.py:173-174
+init_c, init_a     float32 [R,K]               log2(w r), r ts log2(e) of gibbs.py:186-188
+mcweights/mcrates  float64 [R,S,K]             basicrta/gibbs.py:169-170
+indicator          uint8, chain r = [S,N_r]    dense, the reference's layout (gibbs.py:167)
+exchange           1280 B per chain            integer team partials + arrive counter
+=================  ==========================  ==========================================
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _cabi
+from .plan import build_plan
+
+LOG2E = 1.4426950408889634
+
+
+@dataclass
+class ChainInput:
+    """One residue's chain: the reference's ``Gibbs`` inputs in device units."""
+    ticks: np.ndarray                 # integer multiples of ts (any integer dtype)
+    ts: float
+    chain_id: int = 0
+    whypers: np.ndarray = None        # [K]   (default 1/K, gibbs.py:173)
+    rhypers: np.ndarray = None        # [K,2] (default (1,3), gibbs.py:174)
+    init_weights: np.ndarray = None   # [K]   (default gibbs.py:186-188)
+    init_rates: np.ndarray = None     # [K]
+
+
+@dataclass
+class ChainResult:
+    mcweights: np.ndarray = None      # [S,K] float64
+    mcrates: np.ndarray = None        # [S,K] float64
+    indicator: np.ndarray = None      # [S,N] uint8
+    status: int = 0
+    trace_nk: np.ndarray = None       # [niter,K] int64 (FLAG_TRACE)
+    trace_tk: np.ndarray = None
+
+
+def initial_state(ncomp):
+    """Deterministic start of every chain (basicrta/gibbs.py:186-188): rates 5, 0.5, ...
+    descending by decades, weights proportional to 0.9, 0.09, ..."""
+    k = np.arange(ncomp, dtype=np.float64)
+    rates = 0.5 * 10.0 ** (1 - k)
+    weights = 9.0 * 10.0 ** (-(k + 1))
+    return weights / weights.sum(), rates
+
+
+def coefficients(weights, rates, ts):
+    """Logit coefficients in log2 units: logit_k(tick) = c_k - a_k * tick."""
+    w = np.asarray(weights, dtype=np.float64)
+    r = np.asarray(rates, dtype=np.float64)
+    with np.errstate(divide='ignore'):
+        c = np.log2(w) + np.log2(r)
+    a = r * (float(ts) * LOG2E)
+    return c.astype(np.float32), a.astype(np.float32)
+
+
+def times_to_ticks(times, ts):
+    """Residence times -> integer tick counts.  Contact durations are multiples of the
+    trajectory time step (basicrta/contacts.py:222-229); anything else is rounded to the
+    grid and must stay within 1e-3 of a tick."""
+    t = np.asarray(times, dtype=np.float64) / float(ts)
+    ticks = np.rint(t)
+    if len(ticks) and np.max(np.abs(t - ticks)) > 1e-3:
+        raise ValueError('times are not integer multiples of ts; quantise them to the trajectory '
+                         'time step first (basicrta/contacts.py:222-229)')
+    if len(ticks) and (ticks.min() < 0 or ticks.max() >= _cabi.TICK_LIMIT):
+        raise ValueError(f'tick range exceeds [0, 2^23): max {ticks.max():.0f}')
+    return ticks.astype(np.int64)
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise _cabi.BrtaError('basicrta_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+    return torch
+
+
+@dataclass
+class DeviceBatch:
+    """Everything one launch needs, resident on the device."""
+    batch: _cabi.Batch
+    plan: object
+    tensors: dict = field(default_factory=dict)      # keeps device memory alive
+    n_data: np.ndarray = None
+    ind_offset: np.ndarray = None
+    rows: int = 0
+    ncomp: int = 0
+    niter: int = 0
+    flags: int = 0
+    h2d_bytes: int = 0
+    units: float = 0.0                                # sum_r N_r * K * niter
+
+
+class GibbsEngine:
+    """One engine per GPU.  ``prepare`` (pack + H2D), ``launch`` (async kernel),
+    ``fetch`` (D2H) are separate so callers can time and overlap them."""
+
+    def __init__(self, device=0, ctas_per_sm=None, overhead_quads=None):
+        self.torch = _torch()
+        self.lib = _cabi.load()
+        self.device = int(device)
+        self.caps = _cabi.query(self.device)
+        if (self.caps.cc_major, self.caps.cc_minor) != (10, 0):
+            raise _cabi.BrtaError(f'built for sm_100a (B200); device {device} is '
+                                  f'sm_{self.caps.cc_major}{self.caps.cc_minor}')
+        self.ctas_per_sm = ctas_per_sm
+        self.overhead_quads = overhead_quads
+
+    # ---- schedule ----------------------------------------------------------------------
+    def _plan(self, n_data, ncomp, flags, n_waves=None):
+        n_quads = (np.asarray(n_data, dtype=np.int64) + 3) // 4
+        # occupancy is set by registers for small slices; ask with a small slice first,
+        # then shrink the capacity to what that occupancy leaves per CTA.
+        info = _cabi.launch_info(self.device, ncomp, flags, 64)
+        per_sm = info.ctas_per_sm if self.ctas_per_sm is None else min(self.ctas_per_sm, info.ctas_per_sm)
+        if per_sm < 1:
+            raise _cabi.BrtaError('sampler kernel does not fit on an SM')
+        smem_sm = 227 * 1024
+        cap = (smem_sm // per_sm - info.static_smem - 1024) // 16
+        grid = self.caps.sm_count * per_sm
+        kw = {} if self.overhead_quads is None else {'overhead_quads': self.overhead_quads}
+        plan = build_plan(n_quads, grid, cap, n_waves=n_waves, **kw)
+        check = _cabi.launch_info(self.device, ncomp, flags, plan.slice_cap_quads)
+        if check.ctas_per_sm < per_sm:
+            raise _cabi.BrtaError('schedule assumes more co-resident CTAs than the device grants')
+        return plan
+
+    # ---- pack + upload -------------------------------------------------------------------
+    def prepare(self, chains, ncomp, niter, thin=100, seed=0, flags=0, inject=None, n_waves=None):
+        """``chains``: list of :class:`ChainInput`.  ``inject``: dict with optional
+        ``coef_c``/``coef_a`` (list of [niter,K] float32) and ``u`` (list of [niter,N])."""
+        torch = self.torch
+        dev = torch.device('cuda', self.device)
+        R = len(chains)
+        K = int(ncomp)
+        if not 1 <= K <= _cabi.MAX_NCOMP:
+            raise ValueError(f'ncomp must be in 1..{_cabi.MAX_NCOMP}')
+        if niter < 1 or thin < 1:
+            raise ValueError('niter and thin must be >= 1')
+        rows = (niter + 1) // thin
+        n_data = np.array([len(c.ticks) for c in chains], dtype=np.int64)
+        if R == 0 or n_data.min() < 1:
+            raise ValueError('every chain needs at least one datum')
+        if n_data.max() >= (1 << 27):
+            raise ValueError('chain too long (N must be < 2^27)')
+        max_tick = max(int(np.max(c.ticks)) for c in chains)
+        min_tick = min(int(np.min(c.ticks)) for c in chains)
+        if min_tick < 0 or max_tick >= _cabi.TICK_LIMIT:
+            raise ValueError('ticks must lie in [0, 2^23)')
+        tick_dtype = np.uint16 if max_tick < 65536 else np.uint32
+
+        plan = self._plan(n_data, K, flags, n_waves=n_waves)
+        if int(plan.team_size.max()) * int(niter) >= (1 << 31):
+            raise ValueError('team_size * niter overflows the arrive counter')
+
+        pad8 = (n_data + 7) // 8 * 8
+        tick_offset = np.concatenate(([0], np.cumsum(pad8)[:-1])).astype(np.int64)
+        ticks = np.zeros(int(pad8.sum()), dtype=tick_dtype)
+        ts = np.zeros(R, dtype=np.float32)
+        chain_id = np.zeros(R, dtype=np.uint32)
+        whyper = np.zeros((R, K), dtype=np.float32)
+        rhyper = np.zeros((R, K, 2), dtype=np.float32)
+        init_c = np.zeros((R, K), dtype=np.float32)
+        init_a = np.zeros((R, K), dtype=np.float32)
+        w0, r0 = initial_state(K)
+        for r, ch in enumerate(chains):
+            t = np.asarray(ch.ticks)
+            ticks[tick_offset[r]:tick_offset[r] + len(t)] = t
+            ts[r] = ch.ts
+            chain_id[r] = np.uint32(ch.chain_id & 0xFFFFFFFF)
+            whyper[r] = np.ones(K) / K if ch.whypers is None else ch.whypers
+            rhyper[r] = np.ones((K, 2)) * [1.0, 3.0] if ch.rhypers is None else ch.rhypers
+            iw = w0 if ch.init_weights is None else ch.init_weights
+            ir = r0 if ch.init_rates is None else ch.init_rates
+            init_c[r], init_a[r] = coefficients(iw, ir, ch.ts)
+        # per-iteration slice sums are accumulated in 32 bits inside a CTA
+        for task in plan.tasks:
+            r = task['chain']
+            lo = tick_offset[r] + 4 * int(task['quad_begin'])
+            hi = min(lo + 4 * int(task['quad_count']), tick_offset[r] + n_data[r])
+            if int(ticks[lo:hi].sum(dtype=np.int64)) >= (1 << 32):
+                raise ValueError('a slice holds more than 2^32 ticks; use a coarser ts')
+
+        ind_stride = n_data.astype(np.int32)
+        ind_bytes = rows * n_data
+        ind_offset = np.concatenate(([0], np.cumsum(ind_bytes)[:-1])).astype(np.int64)
+
+        T = {}
+        h2d = 0
+
+        def up(name, arr):
+            nonlocal h2d
+            t = torch.from_numpy(np.ascontiguousarray(arr)).to(dev, non_blocking=False)
+            T[name] = t
+            h2d += t.numel() * t.element_size()
+            return t.data_ptr()
+
+        b = _cabi.Batch()
+        b.n_chains, b.ncomp, b.niter, b.thin = R, K, int(niter), int(thin)
+        b.tick_bytes = ticks.dtype.itemsize
+        b.flags = int(flags)
+        b.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        b.ticks = up('ticks', ticks.view(np.int16 if tick_dtype == np.uint16 else np.int32))
+        b.tick_offset = up('tick_offset', tick_offset)
+        b.n_data = up('n_data', n_data.astype(np.int32))
+        b.chain_id = up('chain_id', chain_id.view(np.int32))
+        b.ts = up('ts', ts)
+        b.whyper = up('whyper', whyper)
+        b.rhyper = up('rhyper', rhyper)
+        b.init_c = up('init_c', init_c)
+        b.init_a = up('init_a', init_a)
+        b.ind_offset = up('ind_offset', ind_offset)
+        b.ind_stride = up('ind_stride', ind_stride)
+        b.tasks = up('tasks', plan.tasks.view(np.int32).reshape(-1, 6))
+        b.cta_task_begin = up('cta_task_begin', plan.cta_task_begin)
+        b.grid_ctas = plan.grid
+        b.slice_cap_quads = plan.slice_cap_quads
+
+        def dev_zeros(name, shape, dtype):
+            T[name] = torch.zeros(shape, dtype=dtype, device=dev)
+            return T[name].data_ptr()
+
+        b.mcweights = dev_zeros('mcweights', (R, max(rows, 1), K), torch.float64)
+        b.mcrates = dev_zeros('mcrates', (R, max(rows, 1), K), torch.float64)
+        b.indicator = dev_zeros('indicator', (max(int(ind_bytes.sum()), 1),), torch.uint8)
+        b.status = dev_zeros('status', (R,), torch.int32)
+        b.exchange = dev_zeros('exchange', (R * _cabi.EXCH_STRIDE,), torch.uint8)
+
+        inject = inject or {}
+        if flags & _cabi.FLAG_INJECT_COEF:
+            b.inj_c = up('inj_c', np.stack([np.asarray(x, np.float32).reshape(niter, K) for x in inject['coef_c']]))
+            b.inj_a = up('inj_a', np.stack([np.asarray(x, np.float32).reshape(niter, K) for x in inject['coef_a']]))
+        if flags & _cabi.FLAG_INJECT_U:
+            pitch = (n_data + 3) // 4 * 4
+            u_off = np.concatenate(([0], np.cumsum(pitch * niter)[:-1])).astype(np.int64)
+            u_all = np.zeros(int((pitch * niter).sum()), dtype=np.float32)
+            for r, u in enumerate(inject['u']):
+                blk = u_all[u_off[r]:u_off[r] + pitch[r] * niter].reshape(niter, pitch[r])
+                blk[:, :n_data[r]] = np.asarray(u, np.float32)
+            b.inj_u = up('inj_u', u_all)
+            b.inj_u_offset = up('inj_u_offset', u_off)
+        if flags & _cabi.FLAG_TRACE:
+            b.trace_nk = dev_zeros('trace_nk', (R, niter, K), torch.int64)
+            b.trace_tk = dev_zeros('trace_tk', (R, niter, K), torch.int64)
+
+        return DeviceBatch(batch=b, plan=plan, tensors=T, n_data=n_data, ind_offset=ind_offset,
+                           rows=rows, ncomp=K, niter=int(niter), flags=int(flags), h2d_bytes=h2d,
+                           units=float(n_data.sum()) * K * int(niter))
+
+    # ---- run -----------------------------------------------------------------------------
+    def reset(self, db):
+        """Zero the exchange workspace and status so the same DeviceBatch can be launched again."""
+        db.tensors['exchange'].zero_()
+        db.tensors['status'].zero_()
+
+    def launch(self, db, stream=None):
+        torch = self.torch
+        with torch.cuda.device(self.device):
+            s = torch.cuda.current_stream() if stream is None else stream
+            rc = self.lib.brta_gibbs_run_batch(C.byref(db.batch), C.c_void_p(s.cuda_stream))
+        _cabi.check(rc, 'brta_gibbs_run_batch')
+
+    def fetch(self, db, out=None):
+        """D2H of the results.  Returns a list of :class:`ChainResult`."""
+        torch = self.torch
+        T = db.tensors
+        torch.cuda.synchronize(self.device)
+        status = T['status'].cpu().numpy()
+        mcw = T['mcweights'].cpu().numpy()
+        mcr = T['mcrates'].cpu().numpy()
+        ind = T['indicator'].cpu().numpy()
+        tr_nk = T['trace_nk'].cpu().numpy() if 'trace_nk' in T else None
+        tr_tk = T['trace_tk'].cpu().numpy() if 'trace_tk' in T else None
+        res = []
+        for r, n in enumerate(db.n_data):
+            o = int(db.ind_offset[r])
+            res.append(ChainResult(
+                mcweights=mcw[r, :db.rows].copy(), mcrates=mcr[r, :db.rows].copy(),
+                indicator=ind[o:o + db.rows * int(n)].reshape(db.rows, int(n)),
+                status=int(status[r]),
+                trace_nk=None if tr_nk is None else tr_nk[r],
+                trace_tk=None if tr_tk is None else tr_tk[r]))
+        return res
+
+    def run(self, chains, ncomp, niter, thin=100, seed=0, flags=0, inject=None, n_waves=None):
+        db = self.prepare(chains, ncomp, niter, thin=thin, seed=seed, flags=flags, inject=inject,
+                          n_waves=n_waves)
+        self.launch(db)
+        return self.fetch(db)
+
+
+_engines = {}
+
+
+def get_engine(device=0):
+    if device not in _engines:
+        _engines[device] = GibbsEngine(device)
+    return _engines[device]

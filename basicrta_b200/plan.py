@@ -1,0 +1,167 @@
+"""Static schedule of chains (residues) onto the persistent grid of one GPU.
+
+The reference fans residues out to a ``multiprocessing.Pool`` with ``chunksize=1``
+(basicrta/gibbs.py:73-86): one chain per worker process, greedy dynamic balance.  On a
+B200 one chain cannot fill 148 SMs and 400 chains do not divide evenly over them, so the
+schedule gives every chain a *team* of CTAs sized in proportion to its cost
+(N_r * K * niter; K and niter are common to a batch, so cost ~ N_r):
+
+* chains are grouped into *waves*; inside a wave every CTA of the grid holds at most one
+  task, and team sizes are chosen greedily so that the largest per-CTA slice is as small
+  as possible -- all teams of a wave then finish together, whatever the mix of sizes;
+* the number of waves trades per-iteration rendezvous overhead (small slices) against
+  integer rounding of team sizes (few CTAs per chain); it is picked by a cost model;
+* all members of a team hold their chain in the same wave and every CTA walks its waves
+  in order, which makes the in-kernel rendezvous deadlock-free under a cooperative launch.
+
+Pure NumPy, no GPU needed: the host logic is covered by the CPU test-suite.
+"""
+import heapq
+from dataclasses import dataclass
+
+import numpy as np
+
+TASK_DTYPE = np.dtype([('chain', np.int32), ('team_size', np.int32), ('team_rank', np.int32),
+                       ('quad_begin', np.int32), ('quad_count', np.int32), ('order', np.int32)])
+
+MIN_SLICE_QUADS = 64        # a CTA has 256 threads; below this most of them idle
+DEFAULT_OVERHEAD_QUADS = 192.0   # rendezvous + posterior draw per iteration, in quad-times
+
+
+@dataclass
+class Plan:
+    tasks: np.ndarray            # TASK_DTYPE, grouped by CTA, ascending order within a CTA
+    cta_task_begin: np.ndarray   # int32 [grid + 1]
+    grid: int
+    slice_cap_quads: int         # largest quad_count
+    n_waves: int
+    team_size: np.ndarray        # int32 [R]
+    wave_of_chain: np.ndarray    # int32 [R]
+    est_efficiency: float        # sum(quads) / (grid * sum_w max slice)
+
+    def tasks_of_cta(self, b):
+        return self.tasks[self.cta_task_begin[b]:self.cta_task_begin[b + 1]]
+
+
+def _allocate_wave(quads, cmin, grid):
+    """Team sizes for one wave: start at the minimum, then hand spare CTAs to the team with
+    the largest slice.  Returns (team sizes, largest slice)."""
+    team = cmin.copy()
+    spare = grid - int(team.sum())
+    assert spare >= 0
+    heap = [(-int(-(-int(q) // int(c))), i) for i, (q, c) in enumerate(zip(quads, team))]
+    heapq.heapify(heap)
+    while spare > 0 and heap:
+        negd, i = heapq.heappop(heap)
+        q, c = int(quads[i]), int(team[i]) + 1
+        d = -(-q // c)
+        if d < MIN_SLICE_QUADS:
+            # the largest slice of the wave is already tiny: more CTAs would only add
+            # rendezvous traffic; leave the spare CTAs without a task in this wave
+            heapq.heappush(heap, (negd, i))
+            break
+        team[i] = c
+        spare -= 1
+        heapq.heappush(heap, (-d, i))
+    dmax = max(-(-int(q) // int(c)) for q, c in zip(quads, team))
+    return team, dmax
+
+
+def _group_contiguous(quads_sorted, cmin_sorted, n_waves, grid):
+    """Split the (descending) chain list into n_waves contiguous groups of similar total
+    work, each feasible for one wave (count <= grid, sum of minimum teams <= grid)."""
+    total = float(quads_sorted.sum())
+    groups, start, acc, acc_c = [], 0, 0.0, 0
+    target = total / n_waves
+    for i, (q, c) in enumerate(zip(quads_sorted, cmin_sorted)):
+        full = (acc_c + c > grid) or (i - start >= grid)
+        if i > start and (full or (acc + 0.5 * q > target * (len(groups) + 1) and len(groups) < n_waves - 1)):
+            groups.append((start, i))
+            start, acc_c = i, 0
+        acc += float(q)
+        acc_c += int(c)
+    groups.append((start, len(quads_sorted)))
+    return groups
+
+
+def build_plan(n_quads, grid, cap_quads, overhead_quads=DEFAULT_OVERHEAD_QUADS, n_waves=None):
+    """Schedule chains with ``n_quads[r]`` quads (4 data each) on ``grid`` CTAs whose shared
+    memory holds at most ``cap_quads`` quads."""
+    n_quads = np.asarray(n_quads, dtype=np.int64)
+    R = len(n_quads)
+    if R == 0:
+        raise ValueError('empty batch')
+    if np.any(n_quads < 1):
+        raise ValueError('every chain needs at least one datum')
+    grid = int(grid)
+    cmin = np.maximum(1, -(-n_quads // int(cap_quads))).astype(np.int64)
+    if cmin.max() > grid:
+        raise ValueError(f'a chain needs {int(cmin.max())} CTAs of {cap_quads} quads; grid has {grid}')
+
+    order = np.argsort(-n_quads, kind='stable')
+    qs, cs = n_quads[order], cmin[order]
+    w_min = max(1, -(-R // grid), -(-int(cs.sum()) // grid))
+    if n_waves is not None:
+        candidates = [max(int(n_waves), w_min)]
+    else:
+        w_hi = min(R, max(w_min + 12, 2 * w_min))
+        candidates = sorted(set(range(w_min, w_hi + 1)))
+
+    best = None
+    for W in candidates:
+        groups = _group_contiguous(qs, cs, W, grid)
+        cost, alloc = 0.0, []
+        for (a, b) in groups:
+            team, dmax = _allocate_wave(qs[a:b], cs[a:b], grid)
+            alloc.append(team)
+            cost += dmax + overhead_quads
+        if best is None or cost < best[0] - 1e-9:
+            best = (cost, groups, alloc)
+    cost, groups, alloc = best
+
+    team_size = np.zeros(R, dtype=np.int32)
+    wave_of = np.zeros(R, dtype=np.int32)
+    per_cta = [[] for _ in range(grid)]
+    sum_dmax = 0
+    for w, ((a, b), team) in enumerate(zip(groups, alloc)):
+        cta = 0
+        dmax = 0
+        for local, c in enumerate(team):
+            r = int(order[a + local])
+            q = int(n_quads[r])
+            c = int(c)
+            team_size[r], wave_of[r] = c, w
+            base, rem = divmod(q, c)
+            begin = 0
+            for rank in range(c):
+                cnt = base + (1 if rank < rem else 0)
+                per_cta[cta].append((r, c, rank, begin, cnt, w))
+                begin += cnt
+                dmax = max(dmax, cnt)
+                cta += 1
+        assert cta <= grid
+        sum_dmax += dmax
+
+    flat, begin = [], np.zeros(grid + 1, dtype=np.int32)
+    for bidx, lst in enumerate(per_cta):
+        flat.extend(lst)
+        begin[bidx + 1] = len(flat)
+    tasks = np.array(flat, dtype=TASK_DTYPE)
+    return Plan(tasks=tasks, cta_task_begin=begin, grid=grid,
+                slice_cap_quads=int(tasks['quad_count'].max()), n_waves=len(groups),
+                team_size=team_size, wave_of_chain=wave_of,
+                est_efficiency=float(n_quads.sum()) / (grid * max(sum_dmax, 1)))
+
+
+def shard_chains(costs, n_shards):
+    """Longest-processing-time-first assignment of whole chains to GPUs (no collective:
+    chains are independent, basicrta/gibbs.py:73-86).  Returns a list of index arrays."""
+    costs = np.asarray(costs, dtype=np.float64)
+    loads = [(0.0, s) for s in range(n_shards)]
+    heapq.heapify(loads)
+    shards = [[] for _ in range(n_shards)]
+    for r in np.argsort(-costs, kind='stable'):
+        load, s = heapq.heappop(loads)
+        shards[s].append(int(r))
+        heapq.heappush(loads, (load + float(costs[r]), s))
+    return [np.array(sorted(s), dtype=np.int64) for s in shards]

@@ -1,0 +1,171 @@
+/*
+ * basicrta_b200.h — C ABI of the B200-native Gibbs sampler for basicrta's
+ * exponential-mixture residence-time model.
+ *
+ * The reference (orbeckst/basicrta) is pure Python and has no FFI of its own; the
+ * boundary this library sits behind is the public Python API of
+ * basicrta/gibbs.py.  Each entry point below cites the reference lines it replaces.
+ * A maintainer binds it with ctypes (basicrta_b200/_cabi.py is
+ * that binding).
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no C++/torch types;
+ *   - every pointer inside brta_batch is a DEVICE pointer owned by the caller;
+ *   - calls are asynchronous on the given CUDA stream (a cudaStream_t passed as
+ *     void*); the library allocates nothing and keeps no mutable global state apart
+ *     from a per-thread error string;
+ *   - return value: 0 = ok, < 0 = argument error (BRTA_E_*), > 0 = cudaError_t;
+ *   - nothing throws across the boundary; there is no CPU fallback.
+ */
+#ifndef BASICRTA_B200_H
+#define BASICRTA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BRTA_ABI_VERSION 1
+
+/* compile-time geometry of the sampler kernel */
+#define BRTA_THREADS          256   /* threads per CTA                                  */
+#define BRTA_MAX_NCOMP         32   /* K <= 32 (one warp lane per component)            */
+#define BRTA_TICK_LIMIT  (1u << 23) /* ticks must be < 2^23 (exact in float32)          */
+#define BRTA_EXCH_STRIDE     1280   /* bytes of exchange workspace per chain            */
+
+/* brta_batch.flags */
+#define BRTA_FLAG_EXACT        1u   /* IEEE-only arithmetic (bit-exact vs oracle/gibbs_oracle.py) */
+#define BRTA_FLAG_INJECT_COEF  2u   /* teacher forcing: per-iteration (coef_c, coef_a) rows given  */
+#define BRTA_FLAG_INJECT_U     4u   /* indicator uniforms given instead of the Philox stream       */
+#define BRTA_FLAG_TRACE        8u   /* write (n_k, sum tick_k) of every iteration                  */
+
+/* argument errors */
+#define BRTA_E_NULL      -1
+#define BRTA_E_NCOMP     -2
+#define BRTA_E_RANGE     -3
+#define BRTA_E_PLAN      -4
+#define BRTA_E_DEVICE    -5
+
+/* per-chain status words written by the kernel */
+#define BRTA_STATUS_OK        0
+#define BRTA_STATUS_NONFINITE 1   /* a datum saw a non-finite / zero total probability */
+
+typedef struct brta_caps {
+    int32_t abi_version;
+    int32_t cc_major, cc_minor;
+    int32_t sm_count;
+    int32_t max_smem_per_cta;      /* opt-in dynamic shared memory, bytes */
+    int32_t threads_per_cta;       /* BRTA_THREADS */
+    int32_t max_ncomp;             /* BRTA_MAX_NCOMP */
+    int32_t exch_stride;           /* BRTA_EXCH_STRIDE */
+} brta_caps;
+
+/* How many CTAs of the sampler kernel are co-resident per SM for (ncomp, flags,
+ * slice capacity); the schedule is built for grid = sm_count * ctas_per_sm. */
+typedef struct brta_launch_info {
+    int32_t ctas_per_sm;
+    int32_t regs_per_thread;
+    int32_t static_smem;           /* bytes */
+    int32_t kernel_ncomp;          /* the instantiated K the call is routed to (>= ncomp) */
+} brta_launch_info;
+
+/* One CTA's share of one chain: a contiguous range of "quads" (4 data each). A chain
+ * split over team_size CTAs exchanges integer (n_k, sum tick_k) partials through its
+ * exchange workspace once per iteration. Every CTA walks its tasks in ascending
+ * `order`, and the members of a team all hold the chain at the same order, which is
+ * what makes the in-kernel rendezvous deadlock-free. */
+typedef struct brta_task {
+    int32_t chain;                 /* index into the per-chain arrays                  */
+    int32_t team_size;             /* number of CTAs sharing this chain                */
+    int32_t team_rank;             /* 0 .. team_size-1; rank 0 writes mcweights/mcrates */
+    int32_t quad_begin;            /* first quad of this CTA's slice                   */
+    int32_t quad_count;            /* quads in the slice                               */
+    int32_t order;                 /* global position of the chain in the schedule     */
+} brta_task;
+
+/* A batch of independent chains (residues) run by ONE persistent cooperative launch.
+ *
+ * Replaces the loop of basicrta/gibbs.py:191-217 for every chain of the batch, i.e.
+ * what ParallelGibbs.run (gibbs.py:42-88) fans out to a multiprocessing pool.
+ *
+ * S = (niter + 1) / thin saved rows (gibbs.py:167-170); row j/thin - 1 holds the
+ * post-update (weights, rates) of iteration j and the indicators drawn in iteration j
+ * (gibbs.py:214-217).
+ */
+typedef struct brta_batch {
+    int32_t  n_chains;             /* R                                                 */
+    int32_t  ncomp;                /* K (gibbs.py:133 `ncomp`)                          */
+    int32_t  niter;                /* gibbs.py:133 `niter`                              */
+    int32_t  thin;                 /* gibbs.py:140 `g`                                  */
+    int32_t  tick_bytes;           /* 2: uint16 ticks, 4: uint32 ticks                  */
+    uint32_t flags;                /* BRTA_FLAG_*                                       */
+    uint64_t seed;                 /* Philox key                                        */
+
+    /* inputs, per chain r */
+    const void*     ticks;         /* residence times as integer multiples of ts; chain r
+                                      occupies [tick_offset[r], tick_offset[r]+n_data[r]) ,
+                                      tick_offset a multiple of 8 elements, storage padded
+                                      to a multiple of 4 elements per chain               */
+    const int64_t*  tick_offset;   /* [R] element offsets                                */
+    const int32_t*  n_data;        /* [R] N_r                                            */
+    const uint32_t* chain_id;      /* [R] Philox counter word identifying the chain      */
+    const float*    ts;            /* [R] time step (gibbs.py:147-151)                   */
+    const float*    whyper;        /* [R,K] Dirichlet prior (gibbs.py:173)               */
+    const float*    rhyper;        /* [R,K,2] Gamma prior shape, rate (gibbs.py:174)     */
+    const float*    init_c;        /* [R,K] log2(w_k r_k) of the initial state (gibbs.py:186-188) */
+    const float*    init_a;        /* [R,K] r_k * ts * log2(e) of the initial state      */
+
+    /* outputs */
+    double*         mcweights;     /* [R,S,K] float64 (gibbs.py:169)                     */
+    double*         mcrates;       /* [R,S,K] float64 (gibbs.py:170)                     */
+    uint8_t*        indicator;     /* chain r: S rows of ind_stride[r] bytes at ind_offset[r];
+                                      first N_r bytes of a row are the labels (gibbs.py:167-168);
+                                      ind_stride[r] = N_r gives the reference's dense [S,N] */
+    const int64_t*  ind_offset;    /* [R] byte offsets (any alignment)                   */
+    const int32_t*  ind_stride;    /* [R] row pitch in bytes, >= N_r                     */
+    int32_t*        status;        /* [R] BRTA_STATUS_*                                  */
+
+    /* parity hooks (may be NULL unless the matching flag is set) */
+    const float*    inj_c;         /* [R,niter,K] coefficients used in iteration j at row j-1 */
+    const float*    inj_a;         /* [R,niter,K]                                        */
+    const float*    inj_u;         /* chain r: niter rows of 4*ceil(N_r/4) floats at inj_u_offset[r] */
+    const int64_t*  inj_u_offset;  /* [R] element offsets, multiples of 4                */
+    int64_t*        trace_nk;      /* [R,niter,K] n_k of every iteration                 */
+    int64_t*        trace_tk;      /* [R,niter,K] sum of ticks per component             */
+
+    /* schedule */
+    const brta_task* tasks;        /* tasks of CTA b: tasks[cta_task_begin[b] .. cta_task_begin[b+1]) */
+    const int32_t*   cta_task_begin; /* [grid_ctas + 1]                                  */
+    int32_t          grid_ctas;    /* must equal sm_count * ctas_per_sm or less          */
+    int32_t          slice_cap_quads; /* largest quad_count over all tasks               */
+    void*            exchange;     /* R * BRTA_EXCH_STRIDE bytes, zeroed by the caller   */
+} brta_batch;
+
+/* Device capabilities.  Python side: Gibbs.run needs it to size the schedule. */
+int brta_query(int device, brta_caps* caps);
+
+/* Occupancy of the sampler kernel for this (ncomp, flags, slice capacity). */
+int brta_gibbs_launch_info(int device, int ncomp, uint32_t flags, int slice_cap_quads,
+                           brta_launch_info* info);
+
+/* Run every chain of the batch for niter iterations: gibbs.py:186-217 (loop body) for
+ * each chain; asynchronous on `stream`.  With BRTA_FLAG_INJECT_COEF and thin = 1 the same
+ * call is Gibbs._sample_indicator (gibbs.py:321-334): labels drawn from stored
+ * (mcweights, mcrates) rows without a parameter update. */
+int brta_gibbs_run_batch(const brta_batch* batch, void* stream);
+
+/* Fill out[4*n] with Philox4x32-10 words of counters (x0+i, c1, c2, c3) under key
+ * `seed`: exposes the device generator to the known-answer tests. */
+int brta_philox_fill(uint32_t* out_dev, int64_t n, uint32_t x0, uint32_t c1, uint32_t c2,
+                     uint32_t c3, uint64_t seed, void* stream);
+
+/* Last error message of the calling thread ("" if none). */
+const char* brta_last_error(void);
+
+int brta_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BASICRTA_B200_H */

@@ -1,0 +1,96 @@
+"""Bit-exact parity of the CUDA kernel (EXACT mode, through the C ABI) with the oracle.
+
+Teacher forcing: the oracle's per-iteration coefficient rows are injected, so indicators
+and (n_k, sum tick_k) of EVERY iteration must be identical -- the north star's criterion
+"given identical injected uniforms and gamma draws ... bit-exact".
+"""
+import numpy as np
+import pytest
+
+from basicrta_b200 import _cabi
+from basicrta_b200.engine import ChainInput
+from oracle import gibbs_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # n, true weights, true rates, ncomp, niter, thin
+    (1000, [0.9, 0.09, 0.01], [5, 0.05, 0.001], 15, 30, 10),
+    (3001, [0.6, 0.3, 0.1], [3.0, 0.3, 0.02], 4, 24, 1),
+    (257, [0.5, 0.5], [2.0, 0.1], 2, 20, 5),
+    (5000, [0.9, 0.09, 0.01], [5, 0.05, 0.001], 30, 12, 4),
+    (2500, [0.7, 0.2, 0.1], [4.0, 0.4, 0.01], 7, 16, 4),      # routed to the K=8 kernel (padded)
+]
+
+
+def _oracle_chain(n, w, r, K, niter, thin, seed, chain_id, uniforms=False):
+    times = O.synth_times(n, w, r, seed=seed)
+    ts = O.time_step(times)
+    ticks = O.to_ticks(times, ts)
+    rng = np.random.default_rng(seed + 1000)
+    u = None
+    if uniforms:
+        u = np.random.default_rng(seed + 2000).random((niter, n), dtype=np.float32)
+    ref = O.run_teacher_forced(ticks, ts, K, niter, seed=99, chain_id=chain_id, rng=rng, g=thin,
+                               uniforms=u)
+    return ticks, ts, ref, u
+
+
+@pytest.mark.parametrize('case', CASES)
+def test_exact_teacher_forced_philox(engine, case):
+    n, w, r, K, niter, thin = case
+    chains, refs = [], []
+    for cid in range(3):
+        ticks, ts, ref, _ = _oracle_chain(n + 17 * cid, w, r, K, niter, thin, seed=10 + cid, chain_id=cid + 5)
+        chains.append(ChainInput(ticks=ticks, ts=ts, chain_id=cid + 5))
+        refs.append(ref)
+    flags = _cabi.FLAG_EXACT | _cabi.FLAG_INJECT_COEF | _cabi.FLAG_TRACE
+    res = engine.run(chains, K, niter, thin=thin, seed=99, flags=flags,
+                     inject={'coef_c': [x['coef_c'] for x in refs], 'coef_a': [x['coef_a'] for x in refs]})
+    for got, ref in zip(res, refs):
+        assert got.status == 0
+        np.testing.assert_array_equal(got.trace_nk, ref['nk'])
+        np.testing.assert_array_equal(got.trace_tk, ref['tk'])
+        np.testing.assert_array_equal(got.indicator, ref['indicator'])
+
+
+def test_exact_injected_uniforms(engine):
+    n, K, niter, thin = 1500, 5, 10, 2
+    ticks, ts, ref, u = _oracle_chain(n, [0.8, 0.15, 0.05], [5, 0.5, 0.01], K, niter, thin, seed=3,
+                                      chain_id=1, uniforms=True)
+    flags = _cabi.FLAG_EXACT | _cabi.FLAG_INJECT_COEF | _cabi.FLAG_TRACE | _cabi.FLAG_INJECT_U
+    res = engine.run([ChainInput(ticks=ticks, ts=ts, chain_id=1)], K, niter, thin=thin, seed=0, flags=flags,
+                     inject={'coef_c': [ref['coef_c']], 'coef_a': [ref['coef_a']], 'u': [u]})[0]
+    np.testing.assert_array_equal(res.trace_nk, ref['nk'])
+    np.testing.assert_array_equal(res.trace_tk, ref['tk'])
+    np.testing.assert_array_equal(res.indicator, ref['indicator'])
+
+
+def test_team_size_does_not_change_results(engine):
+    """Philox is keyed by the datum index, so any split of a chain over CTAs gives the same bits."""
+    n, K, niter, thin = 20000, 15, 20, 5
+    ticks, ts, ref, _ = _oracle_chain(n, [0.9, 0.09, 0.01], [5, 0.05, 0.001], K, niter, thin, seed=8, chain_id=2)
+    flags = _cabi.FLAG_EXACT | _cabi.FLAG_INJECT_COEF | _cabi.FLAG_TRACE
+    inj = {'coef_c': [ref['coef_c']], 'coef_a': [ref['coef_a']]}
+    db = engine.prepare([ChainInput(ticks=ticks, ts=ts, chain_id=2)], K, niter, thin=thin, seed=99,
+                        flags=flags, inject=inj)
+    assert db.plan.team_size[0] > 1
+    engine.launch(db)
+    got = engine.fetch(db)[0]
+    np.testing.assert_array_equal(got.trace_nk, ref['nk'])
+    np.testing.assert_array_equal(got.trace_tk, ref['tk'])
+    np.testing.assert_array_equal(got.indicator, ref['indicator'])
+
+
+def test_fast_mode_flip_rate(engine):
+    """FAST (MUFU.EX2 + FMA contraction) differs from EXACT only where a uniform lands within
+    float rounding of a CDF boundary: < 1e-4 of the labels, and the statistics stay close."""
+    n, K, niter, thin = 20000, 15, 20, 1
+    ticks, ts, ref, _ = _oracle_chain(n, [0.9, 0.09, 0.01], [5, 0.05, 0.001], K, niter, thin, seed=4, chain_id=3)
+    flags = _cabi.FLAG_INJECT_COEF | _cabi.FLAG_TRACE
+    inj = {'coef_c': [ref['coef_c']], 'coef_a': [ref['coef_a']]}
+    got = engine.run([ChainInput(ticks=ticks, ts=ts, chain_id=3)], K, niter, thin=thin, seed=99,
+                     flags=flags, inject=inj)[0]
+    flips = np.mean(got.indicator != ref['indicator'])
+    assert flips < 1e-4, flips
+    assert np.abs(got.trace_nk - ref['nk']).max() <= 8
