@@ -14,10 +14,15 @@ SRC = os.path.join(HERE, 'csrc', 'brta_gibbs.cu')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
 ABI_VERSION = 1
-THREADS = 256
+THREADS = 128
 MAX_NCOMP = 32
 TICK_LIMIT = 1 << 23
-EXCH_STRIDE = 1280
+MAILBOX_MAX_TEAM = 32
+
+
+def exch_bytes(team):
+    """BRTA_EXCH_BYTES(team) of include/basicrta_b200.h."""
+    return 2 * team * 32 * 16 if team <= MAILBOX_MAX_TEAM else 1280
 
 FLAG_EXACT = 1
 FLAG_INJECT_COEF = 2
@@ -36,7 +41,7 @@ class Caps(C.Structure):
     _fields_ = [('abi_version', C.c_int32), ('cc_major', C.c_int32), ('cc_minor', C.c_int32),
                 ('sm_count', C.c_int32), ('max_smem_per_cta', C.c_int32),
                 ('threads_per_cta', C.c_int32), ('max_ncomp', C.c_int32),
-                ('exch_stride', C.c_int32)]
+                ('mailbox_max_team', C.c_int32)]
 
 
 class LaunchInfo(C.Structure):
@@ -61,7 +66,7 @@ class Batch(C.Structure):
         ('inj_c', C.c_void_p), ('inj_a', C.c_void_p), ('inj_u', C.c_void_p),
         ('inj_u_offset', C.c_void_p), ('trace_nk', C.c_void_p), ('trace_tk', C.c_void_p),
         ('tasks', C.c_void_p), ('cta_task_begin', C.c_void_p), ('grid_ctas', C.c_int32),
-        ('slice_cap_quads', C.c_int32), ('exchange', C.c_void_p),
+        ('slice_cap_quads', C.c_int32), ('exchange', C.c_void_p), ('exch_offset', C.c_void_p),
     ]
 
 

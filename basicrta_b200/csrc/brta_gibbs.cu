@@ -42,7 +42,8 @@ constexpr int WARPS = THREADS / 32;
 constexpr int EXCH_SUM_OFF = 0;
 constexpr int EXCH_CNT_OFF = 768;
 constexpr int EXCH_ARRIVE_OFF = 1152;
-static_assert(EXCH_ARRIVE_OFF + 4 <= BRTA_EXCH_STRIDE, "exchange layout");
+static_assert(EXCH_ARRIVE_OFF + 4 <= BRTA_EXCH_BYTES(BRTA_MAILBOX_MAX_TEAM + 1), "exchange layout");
+static_assert(WARPS >= 2, "the posterior update uses two warps");
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
 {
@@ -55,6 +56,16 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p)
     unsigned v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ ulonglong2 ld_relaxed_v2(const ulonglong2* p)
+{
+    ulonglong2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_v2(ulonglong2* p, unsigned long long a, unsigned long long b)
+{
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" :: "l"(p), "l"(a), "l"(b) : "memory");
 }
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
 {
@@ -110,7 +121,7 @@ __device__ __forceinline__ int count_le(const float (&cum)[K], float thr)
 
 // Labels of D data at once.  l[d][k] holds the logit, then the running cumulative sum.
 template <int K, int D, bool EXACT>
-__device__ __forceinline__ void draw_labels(const float (&tick)[D], const float (&u)[D],
+__device__ __forceinline__ void draw_labels(const float (&tick)[D], const float (&f12)[D],
                                             const float2* __restrict__ s_coef, int kmax,
                                             int (&lab)[D], bool& bad)
 {
@@ -145,24 +156,121 @@ __device__ __forceinline__ void draw_labels(const float (&tick)[D], const float 
     }
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-        const float thr = EXACT ? __fmul_rn(u[d], cum[d]) : u[d] * cum[d];
+        // u = f12 - 1 is exact, so fma(f12, total, -total) is u * total rounded once: the same
+        // bits as the oracle's float32 product
+        const float thr = __fmaf_rn(f12[d], cum[d], -cum[d]);
         lab[d] = min(count_le<K>(l[d], thr), kmax);
         bad |= !(cum[d] > 0.5f);                           // the max term contributes 1; catches NaN
     }
 }
 
-template <int K, bool EXACT>
-__global__ void __launch_bounds__(THREADS)
-gibbs_sweep_kernel(const brta_batch b)
+// Kernel parameters: the caller's batch plus the Philox key schedule, both in the constant bank.
+struct SweepParams {
+    brta_batch b;
+    RoundKeys rk;
+};
+
+// Shared-memory reductions of one datum: n_k += 1 and, 128 bytes further, the tick
+// accumulator, addressed in the shared window (no generic->shared arithmetic in the loop).
+__device__ __forceinline__ void red_shared_stats(uint32_t cnt_addr, uint32_t tick_bits)
+{
+    asm volatile("red.shared.add.u32 [%0], 1;\n\t"
+                 "red.shared.add.u32 [%0+128], %1;"
+                 :: "r"(cnt_addr), "r"(tick_bits) : "memory");
+}
+
+// float tick + 2^23 has the integer tick in its mantissa: bits = 0x4B000000 + tick (exact for
+// tick < 2^23).  The accumulator adds these bits modulo 2^32 and the bias n * 0x4B000000 is
+// removed afterwards, so the conversion costs one FADD and stays off the XU pipe.
+constexpr uint32_t TICK_BIAS = 0x4B000000u;
+
+// One quad (4 data) of the sweep: labels, statistics, optional label store.
+template <int K, bool EXACT, bool SAVE>
+__device__ __forceinline__ void sweep_quad(const float4 tk, const float4 f12, const float2* __restrict__ s_coef,
+                                           int kmax, int dom, int i0, int n_data, bool partial,
+                                           uint32_t stat_addr, uint8_t* ind_row, bool& bad)
 {
     constexpr int D = (K <= 16) ? 4 : 2;                   // data in flight per thread
+    const float tks[4] = {tk.x, tk.y, tk.z, tk.w};
+    const float fs[4] = {f12.x, f12.y, f12.z, f12.w};      // uniforms as floats in [1,2)
+    int labs[4];
+#pragma unroll
+    for (int h = 0; h < 4; h += D) {
+        float td[D], fd[D];
+        int ld[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) { td[d] = tks[h + d]; fd[d] = fs[h + d]; }
+        draw_labels<K, D, EXACT>(td, fd, s_coef, kmax, ld, bad);
+#pragma unroll
+        for (int d = 0; d < D; ++d) labs[h + d] = ld[d];
+    }
+    if (partial) {                                         // the chain's last quad: padding is never counted
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+            if (i0 + d >= n_data) labs[d] = dom;
+    }
+#pragma unroll
+    for (int d = 0; d < 4; ++d)
+        if (labs[d] != dom)                                // ~10 % of the lanes: ATOMS cost scales with them
+            red_shared_stats(stat_addr + 4u * (uint32_t)labs[d], __float_as_uint(tks[d] + 8388608.0f));
+    if (SAVE) {                                            // 1 iteration in `thin`: dense [S,N] bytes
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+            if (i0 + d < n_data) ind_row[i0 + d] = (uint8_t)labs[d];
+    }
+}
 
+template <int K, bool EXACT, bool SAVE>
+__device__ __forceinline__ void sweep_slice(const float4* __restrict__ s_tick4, const float2* __restrict__ s_coef,
+                                            int nq, int qb, int n_data, int kmax, int dom, uint32_t j,
+                                            uint32_t chain_id, const RoundKeys& rk,
+                                            const float4* __restrict__ u_row, uint32_t stat_addr,
+                                            uint8_t* ind_row, bool& bad)
+{
+    // at most one quad of the whole chain is partial; find out once whether it is in this slice
+    const int tail_q = ((n_data & 3) != 0) ? (n_data >> 2) - qb : -1;
+    for (int q = threadIdx.x; q < nq; q += THREADS) {
+        const float4 tk = s_tick4[q];
+        float4 f12;
+        if (u_row != nullptr) {
+            const float4 uu = u_row[qb + q];
+            f12 = make_float4(uu.x + 1.0f, uu.y + 1.0f, uu.z + 1.0f, uu.w + 1.0f);
+        } else {
+            const Words4 w = philox4x32_10_rk((uint32_t)(qb + q), j, chain_id, 0u, rk);
+            f12 = make_float4(word_to_12(w.x), word_to_12(w.y), word_to_12(w.z), word_to_12(w.w));
+        }
+        sweep_quad<K, EXACT, SAVE>(tk, f12, s_coef, kmax, dom, (qb + q) * 4, n_data, q == tail_q,
+                                   stat_addr, ind_row, bad);
+    }
+}
+
+__device__ __forceinline__ void named_barrier_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+
+// co-resident CTAs per SM the register budget is capped for: the serial section of one
+// CTA (exchange + posterior draw) is hidden by the sweeps of the others
+constexpr int min_ctas(int k) { return k <= 16 ? 512 / THREADS : 384 / THREADS; }
+
+template <int K, bool EXACT>
+__global__ void __launch_bounds__(THREADS, min_ctas(K))
+gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
+{
+    const brta_batch& b = prm.b;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4* s_tick4 = reinterpret_cast<float4*>(smem_raw);
 
     __shared__ __align__(16) float2 s_coef[32];            // {coef_c, coef_a}
-    __shared__ unsigned s_cnt[32];
-    __shared__ unsigned s_sum[32];                         // per-iteration slice sums fit 32 bits (host-checked)
+    // this CTA's statistics of the running iteration: [0..31] n_k, [32..63] biased tick sums
+    // (true sums fit 32 bits: host-checked)
+    __shared__ __align__(16) unsigned s_stat[64];
+    unsigned* const s_cnt = s_stat;
+    unsigned* const s_sum = s_stat + 32;
+    const uint32_t stat_addr = (uint32_t)__cvta_generic_to_shared(s_stat);
+    __shared__ unsigned s_tot_c[WARPS][32];                // team totals, one row per gathering warp
+    __shared__ unsigned long long s_tot_s[WARPS][32];
+    __shared__ float s_rate[32], s_l2r[32];                // warp 1 -> warp 0: rate, log2(rate)
     __shared__ unsigned long long s_red_t[WARPS];
     __shared__ unsigned s_red_n[WARPS];
     __shared__ int s_dom;
@@ -188,6 +296,8 @@ gibbs_sweep_kernel(const brta_batch b)
         const int n_data = b.n_data[r];
         const int nq = task.quad_count;
         const int qb = task.quad_begin;
+        const int team = task.team_size;
+        const bool mailbox = team > 1 && team <= BRTA_MAILBOX_MAX_TEAM;
         const uint32_t chain_id = b.chain_id[r];
         const float ts = b.ts[r];
         const int64_t tick_off = b.tick_offset[r];
@@ -230,23 +340,28 @@ gibbs_sweep_kernel(const brta_batch b)
             s_cnt[tid] = 0;
             s_sum[tid] = 0;
         }
+        s_tot_c[warp][lane] = 0;
+        s_tot_s[warp][lane] = 0;
         if (tid == 0) { s_dom = 0; s_bad = 0; }
         __syncthreads();
 
-        // slice totals and per-component priors live in warp 0's registers
+        // slice totals (warp 0) and per-component priors (warp 0: Dirichlet, warp 1: Gamma)
         unsigned slice_n = 0;
         unsigned long long slice_t = 0;
         float wh = 0.0f, rh_a = 1.0f, rh_b = 1.0f;
         if (warp == 0) {
 #pragma unroll
             for (int w = 0; w < WARPS; ++w) { slice_n += s_red_n[w]; slice_t += s_red_t[w]; }
-            if (lane < kreal) {
-                wh = b.whyper[(size_t)r * kreal + lane];
-                rh_a = b.rhyper[((size_t)r * kreal + lane) * 2 + 0];
-                rh_b = b.rhyper[((size_t)r * kreal + lane) * 2 + 1];
-            }
         }
-        unsigned char* const exch = static_cast<unsigned char*>(b.exchange) + (size_t)r * BRTA_EXCH_STRIDE;
+        if (warp < 2 && lane < kreal) {
+            wh = b.whyper[(size_t)r * kreal + lane];
+            rh_a = b.rhyper[((size_t)r * kreal + lane) * 2 + 0];
+            rh_b = b.rhyper[((size_t)r * kreal + lane) * 2 + 1];
+        }
+        unsigned char* const exch = static_cast<unsigned char*>(b.exchange) + b.exch_offset[r];
+        // mailbox layout: slot[parity][member][32] of {tag<<32 | n_k, tag<<32 | tick sum}
+        ulonglong2* const mbox = reinterpret_cast<ulonglong2*>(exch);
+        // atomics layout (teams larger than the mailbox limit)
         unsigned long long* const ex_sum = reinterpret_cast<unsigned long long*>(exch + EXCH_SUM_OFF);
         unsigned* const ex_cnt = reinterpret_cast<unsigned*>(exch + EXCH_CNT_OFF);
         unsigned* const ex_arrive = reinterpret_cast<unsigned*>(exch + EXCH_ARRIVE_OFF);
@@ -260,112 +375,140 @@ gibbs_sweep_kernel(const brta_batch b)
                 }
                 __syncthreads();
             }
-            const bool save = (j % thin == 0) && (j / thin - 1 < rows);
-            uint8_t* const ind_row = ind_base + (size_t)(save ? j / thin - 1 : 0) * ind_stride;
+            const bool save = (j % thin == 0);
+            const int row = j / thin - 1;
             const float4* const u_row = inject_u
                 ? reinterpret_cast<const float4*>(inj_u_base + (size_t)(j - 1) * u_pitch) : nullptr;
             const int dom = s_dom;
 
             // ---- indicator draws + sufficient statistics (gibbs.py:196-207) -------------
-            for (int q = tid; q < nq; q += THREADS) {
-                const float4 tk = s_tick4[q];
-                const int i0 = (qb + q) * 4;
-                float4 uu;
-                if (inject_u) {
-                    uu = u_row[qb + q];
-                } else {
-                    const Words4 w = philox4x32_10((uint32_t)(qb + q), (uint32_t)j, chain_id, 0u, key0, key1);
-                    uu = make_float4(word_to_unit(w.x), word_to_unit(w.y), word_to_unit(w.z), word_to_unit(w.w));
-                }
-                const float tks[4] = {tk.x, tk.y, tk.z, tk.w};
-                const float us[4] = {uu.x, uu.y, uu.z, uu.w};
-                int labs[4];
-#pragma unroll
-                for (int h = 0; h < 4; h += D) {
-                    float td[D], ud[D];
-                    int ld[D];
-#pragma unroll
-                    for (int d = 0; d < D; ++d) { td[d] = tks[h + d]; ud[d] = us[h + d]; }
-                    draw_labels<K, D, EXACT>(td, ud, s_coef, kreal - 1, ld, bad);
-#pragma unroll
-                    for (int d = 0; d < D; ++d) labs[h + d] = ld[d];
-                }
-#pragma unroll
-                for (int d = 0; d < 4; ++d) {
-                    if (labs[d] != dom && i0 + d < n_data) {
-                        atomicAdd(&s_cnt[labs[d]], 1u);
-                        atomicAdd(&s_sum[labs[d]], __float2uint_rn(tks[d]));
-                    }
-                }
-                if (save) {                                // 1 iteration in `thin`: byte stores, dense [S,N]
-#pragma unroll
-                    for (int d = 0; d < 4; ++d)
-                        if (i0 + d < n_data) ind_row[i0 + d] = (uint8_t)labs[d];
-                }
-            }
+            if (save)
+                sweep_slice<K, EXACT, true>(s_tick4, s_coef, nq, qb, n_data, kreal - 1, dom, (uint32_t)j, chain_id,
+                                            prm.rk, u_row, stat_addr, ind_base + (size_t)row * ind_stride, bad);
+            else
+                sweep_slice<K, EXACT, false>(s_tick4, s_coef, nq, qb, n_data, kreal - 1, dom, (uint32_t)j, chain_id,
+                                             prm.rk, u_row, stat_addr, nullptr, bad);
             __syncthreads();
 
-            // ---- team exchange + posterior update (gibbs.py:210-211): warp 0 ------------
+            // ---- this CTA's partials; the uncounted dominant label follows by subtraction --
             if (warp == 0) {
                 unsigned cnt = s_cnt[lane];
-                unsigned long long sum = (unsigned long long)s_sum[lane];
+                unsigned sum = s_sum[lane] - cnt * TICK_BIAS;   // remove the float-bits bias (mod 2^32)
                 s_cnt[lane] = 0;
                 s_sum[lane] = 0;
-                {   // the dominant label was not counted: recover it from the slice totals
-                    const unsigned oc = __reduce_add_sync(FULL, cnt);
-                    const unsigned long long os = warp_sum_u64(sum);
-                    if (lane == dom) { cnt = slice_n - oc; sum = slice_t - os; }
-                }
-                if (task.team_size > 1) {
+                const unsigned oc = __reduce_add_sync(FULL, cnt);
+                const unsigned os = __reduce_add_sync(FULL, sum);
+                if (lane == dom) { cnt = slice_n - oc; sum = (unsigned)(slice_t - os); }
+                if (team == 1) {
+                    s_tot_c[0][lane] = cnt;
+                    s_tot_s[0][lane] = sum;
+                } else if (mailbox) {
+                    if (lane < kreal) {
+                        const unsigned long long tag = (unsigned long long)(unsigned)j << 32;
+                        st_relaxed_v2(&mbox[((size_t)(j & 1) * team + task.team_rank) * 32 + lane],
+                                      tag | cnt, tag | sum);
+                    }
+                } else {
+                    // large team: L2 atomics + monotonic arrive counter (3 rotating buffers)
                     const int buf = j % 3;
                     if (cnt != 0u) {
                         atomicAdd(&ex_cnt[buf * 32 + lane], cnt);
-                        atomicAdd(&ex_sum[buf * 32 + lane], sum);
+                        atomicAdd(&ex_sum[buf * 32 + lane], (unsigned long long)sum);
                     }
                     __syncwarp();
                     if (lane == 0) {
                         __threadfence();
                         atomicAdd(ex_arrive, 1u);
                     }
-                    const unsigned target = (unsigned)task.team_size * (unsigned)j;
+                    const unsigned target = (unsigned)team * (unsigned)j;
                     while (ld_acquire_u32(ex_arrive) < target) __nanosleep(40);
-                    cnt = ld_relaxed_u32(&ex_cnt[buf * 32 + lane]);
-                    sum = ld_relaxed_u64(&ex_sum[buf * 32 + lane]);
+                    s_tot_c[0][lane] = ld_relaxed_u32(&ex_cnt[buf * 32 + lane]);
+                    s_tot_s[0][lane] = ld_relaxed_u64(&ex_sum[buf * 32 + lane]);
                     if (task.team_rank == 0) {             // recycle the buffer last read in j-1
                         const int old = (j + 2) % 3;
                         ex_cnt[old * 32 + lane] = 0u;
                         ex_sum[old * 32 + lane] = 0ull;
                     }
                 }
-                if (trace && task.team_rank == 0 && lane < kreal) {
-                    const size_t o = ((size_t)r * niter + (j - 1)) * kreal + lane;
-                    b.trace_nk[o] = (int64_t)cnt;
-                    b.trace_tk[o] = (int64_t)sum;
+            }
+            if (mailbox) {
+                // every warp gathers a share of the members: lane = component, all loads of a
+                // round in flight together; a word is valid once it carries this iteration's tag
+                constexpr int MAXM = (BRTA_MAILBOX_MAX_TEAM + WARPS - 1) / WARPS;
+                unsigned acc_c = 0;
+                unsigned long long acc_s = 0;
+                if (lane < kreal) {
+                    const ulonglong2* const base = &mbox[(size_t)(j & 1) * team * 32 + lane];
+                    unsigned pend = 0;
+#pragma unroll
+                    for (int i = 0; i < MAXM; ++i)
+                        if (warp + i * WARPS < team) pend |= 1u << i;
+                    while (pend) {
+                        ulonglong2 v[MAXM];
+#pragma unroll
+                        for (int i = 0; i < MAXM; ++i)
+                            if (pend & (1u << i)) v[i] = ld_relaxed_v2(&base[(size_t)(warp + i * WARPS) * 32]);
+#pragma unroll
+                        for (int i = 0; i < MAXM; ++i) {
+                            if ((pend & (1u << i)) && (unsigned)(v[i].x >> 32) == (unsigned)j &&
+                                (unsigned)(v[i].y >> 32) == (unsigned)j) {
+                                acc_c += (unsigned)v[i].x;
+                                acc_s += (unsigned)v[i].y;
+                                pend &= ~(1u << i);
+                            }
+                        }
+                        if (pend) __nanosleep(20);
+                    }
                 }
-                // next iteration skips the most populated label in the atomics
-                {
-                    const unsigned keyv = (lane < kreal) ? ((cnt << 5) | (unsigned)(31 - lane)) : 0u;
+                s_tot_c[warp][lane] = acc_c;
+                s_tot_s[warp][lane] = acc_s;
+            }
+            __syncthreads();
+
+            // ---- posterior update (gibbs.py:210-211): warp 0 weights, warp 1 rates ----------
+            if (warp < 2) {
+                unsigned cnt = 0;
+                unsigned long long sum = 0;
+#pragma unroll
+                for (int w = 0; w < WARPS; ++w) { cnt += s_tot_c[w][lane]; sum += s_tot_s[w][lane]; }
+                const bool live = lane < kreal;
+                if (warp == 0) {
+                    if (trace && task.team_rank == 0 && live) {
+                        const size_t o = ((size_t)r * niter + (j - 1)) * kreal + lane;
+                        b.trace_nk[o] = (int64_t)cnt;
+                        b.trace_tk[o] = (int64_t)sum;
+                    }
+                    // next iteration skips the most populated label in the atomics
+                    const unsigned keyv = live ? ((cnt << 5) | (unsigned)(31 - lane)) : 0u;
                     const unsigned best = __reduce_max_sync(FULL, keyv);
                     if (lane == 0) s_dom = 31 - (int)(best & 31u);
                 }
                 if (!inject_coef) {
-                    const bool live = lane < kreal;
                     const float fcnt = (float)cnt;
-                    float lgw = -INFINITY, lgr = 0.0f;
-                    if (live) {
-                        lgw = log_gamma_draw(wh + fcnt, (uint32_t)j, chain_id, 1u + 4u * lane, key0, key1);
-                        lgr = log_gamma_draw(rh_a + fcnt, (uint32_t)j, chain_id, 2u + 4u * lane, key0, key1)
-                              - logf(fmaf((float)sum, ts, rh_b));
+                    if (warp == 1) {
+                        float rate = 0.0f;
+                        if (live) {
+                            const float g = gamma_draw(rh_a + fcnt, (uint32_t)j, chain_id, 2u + 4u * lane, key0, key1);
+                            rate = g / fmaf((float)sum, ts, rh_b);
+                        }
+                        s_rate[lane] = rate;
+                        s_l2r[lane] = __log2f(rate);
                     }
-                    const float mx = warp_max(lgw);
-                    const float tot = warp_sum(live ? expf(lgw - mx) : 0.0f);
-                    const float lnw = lgw - mx - logf(tot);
-                    const float rate = expf(lgr);
-                    if (live) s_coef[lane] = make_float2((lnw + lgr) * LOG2E, rate * (ts * LOG2E));
-                    if (save && task.team_rank == 0 && live) {
-                        const size_t o = ((size_t)r * rows + (j / thin - 1)) * kreal + lane;
-                        b.mcweights[o] = exp((double)lnw);
-                        b.mcrates[o] = (double)rate;
+                    float l2y = -INFINITY;
+                    if (warp == 0 && live)
+                        l2y = gamma_log2_draw(wh + fcnt, (uint32_t)j, chain_id, 1u + 4u * lane, key0, key1);
+                    named_barrier_sync(1, 64);
+                    if (warp == 0) {
+                        const float mx = warp_max(l2y);
+                        const float tot = warp_sum(live ? fast_exp2(l2y - mx) : 0.0f);
+                        const float l2w = l2y - mx - __log2f(tot);
+                        const float rate = s_rate[lane];
+                        if (live) s_coef[lane] = make_float2(l2w + s_l2r[lane], rate * (ts * LOG2E));
+                        if (save && task.team_rank == 0 && live && row < rows) {
+                            const size_t o = ((size_t)r * rows + row) * kreal + lane;
+                            b.mcweights[o] = exp2((double)l2w);
+                            b.mcrates[o] = (double)rate;
+                        }
                     }
                 }
             }
@@ -401,7 +544,7 @@ int cuda_fail(cudaError_t e, const char* where)
     return (int)e;
 }
 
-typedef void (*kernel_fn)(const brta_batch);
+typedef void (*kernel_fn)(const SweepParams);
 
 struct Variant { int k; kernel_fn fast; kernel_fn exact; };
 
@@ -440,7 +583,7 @@ int brta_query(int device, brta_caps* caps)
     caps->max_smem_per_cta = (int32_t)p.sharedMemPerBlockOptin;
     caps->threads_per_cta = BRTA_THREADS;
     caps->max_ncomp = BRTA_MAX_NCOMP;
-    caps->exch_stride = BRTA_EXCH_STRIDE;
+    caps->mailbox_max_team = BRTA_MAILBOX_MAX_TEAM;
     return 0;
 }
 
@@ -481,7 +624,7 @@ int brta_gibbs_run_batch(const brta_batch* batch, void* stream)
         return brta::fail(BRTA_E_RANGE, "tick_bytes must be 2 or 4");
     if (!b.ticks || !b.tick_offset || !b.n_data || !b.chain_id || !b.ts || !b.whyper || !b.rhyper ||
         !b.indicator || !b.ind_offset || !b.ind_stride || !b.status || !b.tasks ||
-        !b.cta_task_begin || !b.exchange)
+        !b.cta_task_begin || !b.exchange || !b.exch_offset)
         return brta::fail(BRTA_E_NULL, "brta_gibbs_run_batch: a required pointer is NULL");
     if (b.flags & BRTA_FLAG_INJECT_COEF) {
         if (!b.inj_c || !b.inj_a) return brta::fail(BRTA_E_NULL, "INJECT_COEF needs inj_c and inj_a");
@@ -497,7 +640,10 @@ int brta_gibbs_run_batch(const brta_batch* batch, void* stream)
     const size_t smem = (size_t)b.slice_cap_quads * 16;
     cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return brta::cuda_fail(e, "cudaFuncSetAttribute(smem)");
-    void* args[] = {(void*)batch};
+    brta::SweepParams prm;
+    prm.b = b;
+    prm.rk = brta::philox_round_keys(b.seed);
+    void* args[] = {(void*)&prm};
     e = cudaLaunchCooperativeKernel((const void*)fn, dim3((unsigned)b.grid_ctas), dim3(BRTA_THREADS), args,
                                     smem, (cudaStream_t)stream);
     if (e != cudaSuccess) return brta::cuda_fail(e, "cudaLaunchCooperativeKernel");

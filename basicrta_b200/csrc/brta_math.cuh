@@ -61,40 +61,64 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
     return v;
 }
 
-// ---- log of a Gamma(shape, 1) variate -------------------------------------------------
-// Marsaglia & Tsang (2000) with the shape < 1 boost G(a) = G(a+1) U^(1/a), carried out in
-// log space: an empty component has Dirichlet shape 1/K (gibbs.py:173), where U^K
-// underflows float32; the sampler only ever needs log w_k.
-// One Philox call per trial: words 0,1 -> Box-Muller normal, 2 -> accept uniform,
-// 3 -> boost uniform.
-__device__ __forceinline__ float log_gamma_draw(float shape, uint32_t iter, uint32_t chain,
-                                                uint32_t purpose, uint32_t k0, uint32_t k1)
+// ---- Gamma(shape, 1) variates ---------------------------------------------------------
+// Marsaglia & Tsang (2000).  One Philox call per trial: words 0,1 -> Box-Muller normal,
+// 2 -> accept uniform, 3 -> boost uniform.  The squeeze test accepts ~92 % of the trials
+// without a logarithm; the exact test needs log(v) accurately (v is within 1e-3 of 1 for
+// the large shapes 1 + n_k), hence log1pf there and MUFU-grade intrinsics elsewhere.
+// Returns d*v with d = a - 1/3 for the (possibly boosted) shape a >= 1.
+__device__ __forceinline__ float gamma_core(float a, uint32_t iter, uint32_t chain, uint32_t purpose,
+                                            uint32_t k0, uint32_t k1, uint32_t& boost_word)
 {
-    const bool boost = shape < 1.0f;
-    const float a = boost ? shape + 1.0f : shape;
     const float d = a - (1.0f / 3.0f);
     const float c = rsqrtf(9.0f * d);
-    float result = logf(d);                               // fallback: the mode (never in practice)
+    float result = d;                                     // fallback: never reached in practice
+    boost_word = 0x80000000u;
     for (uint32_t trial = 0; trial < 64u; ++trial) {
         const Words4 w = philox4x32_10(trial, iter, chain, purpose, k0, k1);
         const float u1 = word_to_unit_open_low(w.x);
         const float u2 = word_to_unit(w.y);
-        const float z = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
-        float v = fmaf(c, z, 1.0f);
-        if (v <= 0.0f) continue;
-        v = v * v * v;
+        const float z = sqrtf(-2.0f * __logf(u1)) * __cosf(6.283185307179586f * u2);
+        const float x = c * z;
+        if (x <= -1.0f) continue;
+        const float t = 1.0f + x;
+        const float v = t * t * t;
         const float u = word_to_unit_open(w.z);
         const float z2 = z * z;
-        const float logv = logf(v);
-        const bool ok = (u < 1.0f - 0.0331f * z2 * z2) ||
-                        (logf(u) < 0.5f * z2 + d * (1.0f - v + logv));
+        bool ok = u < 1.0f - 0.0331f * z2 * z2;
+        if (!ok) ok = __logf(u) < 0.5f * z2 + d * (1.0f - v + 3.0f * log1pf(x));
         if (ok) {
-            result = logf(d) + logv;
-            if (boost) result += logf(word_to_unit_open_low(w.w)) / shape;
+            result = d * v;
+            boost_word = w.w;
             break;
         }
     }
     return result;
+}
+
+// Gamma(shape, 1) in linear space (rates: shape = 1 + n_k >= 1 with the default prior).
+__device__ __forceinline__ float gamma_draw(float shape, uint32_t iter, uint32_t chain, uint32_t purpose,
+                                            uint32_t k0, uint32_t k1)
+{
+    const bool boost = shape < 1.0f;
+    uint32_t bw;
+    float g = gamma_core(boost ? shape + 1.0f : shape, iter, chain, purpose, k0, k1, bw);
+    if (boost) g *= fast_exp2(__log2f(word_to_unit_open_low(bw)) / shape);
+    return g;
+}
+
+// log2 of a Gamma(shape, 1) variate.  The shape < 1 boost G(a) = G(a+1) U^(1/a) stays in
+// log space: an empty component has Dirichlet shape 1/K (gibbs.py:173), where U^K
+// underflows float32; the sampler only ever needs log w_k.
+__device__ __forceinline__ float gamma_log2_draw(float shape, uint32_t iter, uint32_t chain,
+                                                 uint32_t purpose, uint32_t k0, uint32_t k1)
+{
+    const bool boost = shape < 1.0f;
+    uint32_t bw;
+    const float g = gamma_core(boost ? shape + 1.0f : shape, iter, chain, purpose, k0, k1, bw);
+    float l2 = __log2f(g);
+    if (boost) l2 += __log2f(word_to_unit_open_low(bw)) / shape;
+    return l2;
 }
 
 }  // namespace brta

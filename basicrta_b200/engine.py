@@ -17,7 +17,7 @@ whyper, rhyper     float32 [R,K], [R,K,2]      basicrta/gibbs.py:173-174
 init_c, init_a     float32 [R,K]               log2(w r), r ts log2(e) of gibbs.py:186-188
 mcweights/mcrates  float64 [R,S,K]             basicrta/gibbs.py:169-170
 indicator          uint8, chain r = [S,N_r]    dense, the reference's layout (gibbs.py:167)
-exchange           1280 B per chain            integer team partials + arrive counter
+exchange           BRTA_EXCH_BYTES(team)/chain tagged mailboxes of integer team partials
 =================  ==========================  ==========================================
 """
 import ctypes as C
@@ -242,7 +242,10 @@ class GibbsEngine:
         b.mcrates = dev_zeros('mcrates', (R, max(rows, 1), K), torch.float64)
         b.indicator = dev_zeros('indicator', (max(int(ind_bytes.sum()), 1),), torch.uint8)
         b.status = dev_zeros('status', (R,), torch.int32)
-        b.exchange = dev_zeros('exchange', (R * _cabi.EXCH_STRIDE,), torch.uint8)
+        exch_size = np.array([(_cabi.exch_bytes(int(c)) + 127) // 128 * 128 for c in plan.team_size], dtype=np.int64)
+        exch_offset = np.concatenate(([0], np.cumsum(exch_size)[:-1])).astype(np.int64)
+        b.exchange = dev_zeros('exchange', (int(exch_size.sum()),), torch.uint8)
+        b.exch_offset = up('exch_offset', exch_offset)
 
         inject = inject or {}
         if flags & _cabi.FLAG_INJECT_COEF:

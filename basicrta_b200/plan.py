@@ -24,7 +24,7 @@ import numpy as np
 TASK_DTYPE = np.dtype([('chain', np.int32), ('team_size', np.int32), ('team_rank', np.int32),
                        ('quad_begin', np.int32), ('quad_count', np.int32), ('order', np.int32)])
 
-MIN_SLICE_QUADS = 64        # a CTA has 256 threads; below this most of them idle
+MIN_SLICE_QUADS = 32        # a CTA has 128 threads; below this most of them idle
 DEFAULT_OVERHEAD_QUADS = 192.0   # rendezvous + posterior draw per iteration, in quad-times
 
 

@@ -29,10 +29,16 @@ extern "C" {
 #define BRTA_ABI_VERSION 1
 
 /* compile-time geometry of the sampler kernel */
-#define BRTA_THREADS          256   /* threads per CTA                                  */
+#ifndef BRTA_THREADS
+#define BRTA_THREADS          128   /* threads per CTA                                  */
+#endif
 #define BRTA_MAX_NCOMP         32   /* K <= 32 (one warp lane per component)            */
 #define BRTA_TICK_LIMIT  (1u << 23) /* ticks must be < 2^23 (exact in float32)          */
-#define BRTA_EXCH_STRIDE     1280   /* bytes of exchange workspace per chain            */
+#define BRTA_MAILBOX_MAX_TEAM   32   /* teams up to this size exchange through tagged mailboxes */
+/* bytes of exchange workspace of a chain run by `team` CTAs (zeroed by the caller):
+ * mailbox teams: 2 parities x team x 32 components x 16 B; larger teams: 3 x 32 x (8+4) B
+ * of L2 atomics accumulators + an arrive counter */
+#define BRTA_EXCH_BYTES(team) ((team) <= BRTA_MAILBOX_MAX_TEAM ? 2 * (team) * 32 * 16 : 1280)
 
 /* brta_batch.flags */
 #define BRTA_FLAG_EXACT        1u   /* IEEE-only arithmetic (bit-exact vs oracle/gibbs_oracle.py) */
@@ -58,7 +64,7 @@ typedef struct brta_caps {
     int32_t max_smem_per_cta;      /* opt-in dynamic shared memory, bytes */
     int32_t threads_per_cta;       /* BRTA_THREADS */
     int32_t max_ncomp;             /* BRTA_MAX_NCOMP */
-    int32_t exch_stride;           /* BRTA_EXCH_STRIDE */
+    int32_t mailbox_max_team;      /* BRTA_MAILBOX_MAX_TEAM */
 } brta_caps;
 
 /* How many CTAs of the sampler kernel are co-resident per SM for (ncomp, flags,
@@ -129,7 +135,8 @@ typedef struct brta_batch {
     /* parity hooks (may be NULL unless the matching flag is set) */
     const float*    inj_c;         /* [R,niter,K] coefficients used in iteration j at row j-1 */
     const float*    inj_a;         /* [R,niter,K]                                        */
-    const float*    inj_u;         /* chain r: niter rows of 4*ceil(N_r/4) floats at inj_u_offset[r] */
+    const float*    inj_u;         /* chain r: niter rows of 4*ceil(N_r/4) floats at inj_u_offset[r];
+                                      values in [0,1) on the 2^-23 grid the Philox path produces */
     const int64_t*  inj_u_offset;  /* [R] element offsets, multiples of 4                */
     int64_t*        trace_nk;      /* [R,niter,K] n_k of every iteration                 */
     int64_t*        trace_tk;      /* [R,niter,K] sum of ticks per component             */
@@ -139,7 +146,9 @@ typedef struct brta_batch {
     const int32_t*   cta_task_begin; /* [grid_ctas + 1]                                  */
     int32_t          grid_ctas;    /* must equal sm_count * ctas_per_sm or less          */
     int32_t          slice_cap_quads; /* largest quad_count over all tasks               */
-    void*            exchange;     /* R * BRTA_EXCH_STRIDE bytes, zeroed by the caller   */
+    void*            exchange;     /* zeroed by the caller; chain r owns BRTA_EXCH_BYTES(team_size)
+                                      bytes at exch_offset[r]                             */
+    const int64_t*   exch_offset;  /* [R] byte offsets, multiples of 128                 */
 } brta_batch;
 
 /* Device capabilities.  Python side: Gibbs.run needs it to size the schedule. */

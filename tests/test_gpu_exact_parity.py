@@ -30,7 +30,9 @@ def _oracle_chain(n, w, r, K, niter, thin, seed, chain_id, uniforms=False):
     rng = np.random.default_rng(seed + 1000)
     u = None
     if uniforms:
-        u = np.random.default_rng(seed + 2000).random((niter, n), dtype=np.float32)
+        # on the 2^-23 grid the Philox path produces (brta_batch.inj_u contract)
+        u = (np.random.default_rng(seed + 2000).integers(0, 1 << 23, size=(niter, n)).astype(np.float32)
+             * np.float32(2.0 ** -23))
     ref = O.run_teacher_forced(ticks, ts, K, niter, seed=99, chain_id=chain_id, rng=rng, g=thin,
                                uniforms=u)
     return ticks, ts, ref, u
