@@ -9,7 +9,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libbrta_gibbs.so')
+LIB_PATH = os.environ.get('BRTA_LIB', os.path.join(HERE, 'libbrta_gibbs.so'))   # BRTA_LIB: developer override
 SRC = os.path.join(HERE, 'csrc', 'brta_gibbs.cu')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
@@ -71,7 +71,7 @@ class Batch(C.Structure):
 
 
 EXPORTS = ('brta_abi_version', 'brta_last_error', 'brta_query', 'brta_gibbs_launch_info',
-           'brta_gibbs_run_batch', 'brta_philox_fill')
+           'brta_gibbs_run_batch', 'brta_philox_fill', 'brta_mufu_probe')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
@@ -112,6 +112,7 @@ def load():
     lib.brta_gibbs_run_batch.argtypes = [C.POINTER(Batch), C.c_void_p]
     lib.brta_philox_fill.argtypes = [C.c_void_p, C.c_int64, C.c_uint32, C.c_uint32, C.c_uint32,
                                      C.c_uint32, C.c_uint64, C.c_void_p]
+    lib.brta_mufu_probe.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     for name in EXPORTS:
         getattr(lib, name)
     if lib.brta_abi_version() != ABI_VERSION:

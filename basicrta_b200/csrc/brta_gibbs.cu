@@ -244,6 +244,19 @@ __device__ __forceinline__ void sweep_slice(const float4* __restrict__ s_tick4, 
     }
 }
 
+// Developer-only phase timing (-DBRTA_PHASE_TIMING builds libbrta_gibbs_dbg.so): thread 0 of
+// every CTA accumulates clock64 deltas per phase into g_phase[blockIdx.x][8].
+#ifdef BRTA_PHASE_TIMING
+__device__ unsigned long long* g_phase = nullptr;
+#define PHASE_DECL long long ph_t = clock64(); unsigned long long ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define PHASE_MARK(i) do { if (threadIdx.x == 0) { const long long now = clock64(); ph_acc[i] += (unsigned long long)(now - ph_t); ph_t = now; } } while (0)
+#define PHASE_FLUSH do { if (threadIdx.x == 0 && g_phase) for (int i = 0; i < 8; ++i) g_phase[blockIdx.x * 8 + i] += ph_acc[i]; } while (0)
+#else
+#define PHASE_DECL
+#define PHASE_MARK(i)
+#define PHASE_FLUSH
+#endif
+
 __device__ __forceinline__ void named_barrier_sync(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
@@ -367,6 +380,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
         unsigned* const ex_arrive = reinterpret_cast<unsigned*>(exch + EXCH_ARRIVE_OFF);
 
         bool bad = false;
+        PHASE_DECL
         for (int j = 1; j <= niter; ++j) {
             if (inject_coef) {
                 if (tid < kreal) {
@@ -388,7 +402,9 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
             else
                 sweep_slice<K, EXACT, false>(s_tick4, s_coef, nq, qb, n_data, kreal - 1, dom, (uint32_t)j, chain_id,
                                              prm.rk, u_row, stat_addr, nullptr, bad);
+            PHASE_MARK(0);                                 // sweep
             __syncthreads();
+            PHASE_MARK(1);                                 // wait for the CTA's slowest warp
 
             // ---- this CTA's partials; the uncounted dominant label follows by subtraction --
             if (warp == 0) {
@@ -431,6 +447,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
                     }
                 }
             }
+            PHASE_MARK(2);                                 // partials + post
             if (mailbox) {
                 // every warp gathers a share of the members: lane = component, all loads of a
                 // round in flight together; a word is valid once it carries this iteration's tag
@@ -463,7 +480,9 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
                 s_tot_c[warp][lane] = acc_c;
                 s_tot_s[warp][lane] = acc_s;
             }
+            PHASE_MARK(3);                                 // gather (waits for the team's slowest member)
             __syncthreads();
+            PHASE_MARK(4);
 
             // ---- posterior update (gibbs.py:210-211): warp 0 weights, warp 1 rates ----------
             if (warp < 2) {
@@ -497,6 +516,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
                     float l2y = -INFINITY;
                     if (warp == 0 && live)
                         l2y = gamma_log2_draw(wh + fcnt, (uint32_t)j, chain_id, 1u + 4u * lane, key0, key1);
+                    PHASE_MARK(5);                             // gamma draws
                     named_barrier_sync(1, 64);
                     if (warp == 0) {
                         const float mx = warp_max(l2y);
@@ -512,8 +532,11 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
                     }
                 }
             }
+            PHASE_MARK(6);                                 // normalise + coefficients
             __syncthreads();
+            PHASE_MARK(7);
         }
+        PHASE_FLUSH;
         if (bad) atomicOr(&s_bad, 1u);
         __syncthreads();
         if (tid == 0 && s_bad) atomicOr(reinterpret_cast<unsigned*>(&b.status[r]), (unsigned)BRTA_STATUS_NONFINITE);
@@ -528,6 +551,24 @@ __global__ void philox_fill_kernel(uint32_t* out, int64_t n, uint32_t x0, uint32
     if (i >= n) return;
     const Words4 w = philox4x32_10(x0 + (uint32_t)i, c1, c2, c3, k0, k1);
     reinterpret_cast<uint4*>(out)[i] = make_uint4(w.x, w.y, w.z, w.w);
+}
+
+// MUFU.EX2 throughput probe: the measured denominator of the sampler's roofline.  Eight
+// independent ex2 chains per thread, no memory traffic; the result is stored so the loop
+// cannot be removed.
+__global__ void __launch_bounds__(256) mufu_probe_kernel(float* sink, int iters)
+{
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = -1.0e-3f * (float)(threadIdx.x + i + 1);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = fast_exp2(x[i]) - 1.0f;       // 1 MUFU + 1 FADD
+    }
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc += x[i];
+    if (acc == 12345.678f) sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
 // ---- host side ----------------------------------------------------------------------
@@ -649,6 +690,25 @@ int brta_gibbs_run_batch(const brta_batch* batch, void* stream)
     if (e != cudaSuccess) return brta::cuda_fail(e, "cudaLaunchCooperativeKernel");
     return 0;
 }
+
+int brta_mufu_probe(float* sink_dev, int blocks, int iters, void* stream)
+{
+    if (!sink_dev) return brta::fail(BRTA_E_NULL, "brta_mufu_probe: sink is NULL");
+    if (blocks < 1 || iters < 1) return brta::fail(BRTA_E_RANGE, "brta_mufu_probe: blocks, iters >= 1");
+    brta::mufu_probe_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(sink_dev, iters);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return brta::cuda_fail(e, "mufu_probe_kernel");
+    return 0;
+}
+
+#ifdef BRTA_PHASE_TIMING
+int brta_debug_set_phase_buffer(void* dev_ptr)
+{
+    unsigned long long* p = (unsigned long long*)dev_ptr;
+    cudaError_t e = cudaMemcpyToSymbol(brta::g_phase, &p, sizeof(p));
+    return (int)e;
+}
+#endif
 
 int brta_philox_fill(uint32_t* out_dev, int64_t n, uint32_t x0, uint32_t c1, uint32_t c2, uint32_t c3,
                      uint64_t seed, void* stream)

@@ -99,6 +99,7 @@ class DeviceBatch:
     batch: _cabi.Batch
     plan: object
     tensors: dict = field(default_factory=dict)      # keeps device memory alive
+    host: dict = field(default_factory=dict)         # pinned host copies of the inputs
     n_data: np.ndarray = None
     ind_offset: np.ndarray = None
     rows: int = 0
@@ -206,9 +207,15 @@ class GibbsEngine:
         T = {}
         h2d = 0
 
+        H = {}
+
         def up(name, arr):
             nonlocal h2d
-            t = torch.from_numpy(np.ascontiguousarray(arr)).to(dev, non_blocking=False)
+            src = torch.from_numpy(np.ascontiguousarray(arr))
+            pinned = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+            pinned.copy_(src)
+            H[name] = pinned
+            t = pinned.to(dev, non_blocking=True)
             T[name] = t
             h2d += t.numel() * t.element_size()
             return t.data_ptr()
@@ -264,7 +271,8 @@ class GibbsEngine:
             b.trace_nk = dev_zeros('trace_nk', (R, niter, K), torch.int64)
             b.trace_tk = dev_zeros('trace_tk', (R, niter, K), torch.int64)
 
-        return DeviceBatch(batch=b, plan=plan, tensors=T, n_data=n_data, ind_offset=ind_offset,
+        torch.cuda.current_stream(dev).synchronize()
+        return DeviceBatch(batch=b, plan=plan, tensors=T, host=H, n_data=n_data, ind_offset=ind_offset,
                            rows=rows, ncomp=K, niter=int(niter), flags=int(flags), h2d_bytes=h2d,
                            units=float(n_data.sum()) * K * int(niter))
 
@@ -280,6 +288,39 @@ class GibbsEngine:
             s = torch.cuda.current_stream() if stream is None else stream
             rc = self.lib.brta_gibbs_run_batch(C.byref(db.batch), C.c_void_p(s.cuda_stream))
         _cabi.check(rc, 'brta_gibbs_run_batch')
+
+    # ---- host <-> device legs, separately callable so they can be timed / overlapped -------
+    def upload(self, db):
+        """H2D of every input from its pinned host copy (async on the current stream)."""
+        for name, pinned in db.host.items():
+            db.tensors[name].copy_(pinned, non_blocking=True)
+        return db.h2d_bytes
+
+    def alloc_host_outputs(self, db):
+        """Pinned host buffers for the results of ``db`` (reused across runs)."""
+        torch = self.torch
+        return {name: torch.empty(db.tensors[name].shape, dtype=db.tensors[name].dtype, pin_memory=True)
+                for name in ('mcweights', 'mcrates', 'indicator', 'status')}
+
+    def download(self, db, host_out):
+        """D2H of the results into pinned buffers (async on the current stream); returns bytes."""
+        n = 0
+        for name, dst in host_out.items():
+            dst.copy_(db.tensors[name], non_blocking=True)
+            n += dst.numel() * dst.element_size()
+        return n
+
+    def results_from_host(self, db, host_out):
+        """Views (no copy) of pinned result buffers as per-chain arrays."""
+        mcw, mcr = host_out['mcweights'].numpy(), host_out['mcrates'].numpy()
+        ind, status = host_out['indicator'].numpy(), host_out['status'].numpy()
+        res = []
+        for r, n in enumerate(db.n_data):
+            o = int(db.ind_offset[r])
+            res.append(ChainResult(mcweights=mcw[r, :db.rows], mcrates=mcr[r, :db.rows],
+                                   indicator=ind[o:o + db.rows * int(n)].reshape(db.rows, int(n)),
+                                   status=int(status[r])))
+        return res
 
     def fetch(self, db, out=None):
         """D2H of the results.  Returns a list of :class:`ChainResult`."""

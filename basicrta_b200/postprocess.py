@@ -1,0 +1,132 @@
+"""Host-side posterior processing of a finished chain, without the plotting.
+
+The north star keeps this on the host ("process_gibbs and its GaussianMixture clustering,
+tau estimates ... stay on the host").  It is the *consumer* of the sampler's arrays and is
+what the statistical parity tests compare on: clustered weights / rates and the slowest
+tau.  Restates, plot-free:
+
+* ``Gibbs.cluster``          basicrta/gibbs.py:221-273
+* ``Gibbs.process_gibbs``    basicrta/gibbs.py:275-308 (its ``mixture_and_plot`` call only
+                             contributes the label re-sorting of basicrta/util.py:738-756)
+* ``Gibbs._estimate_params`` basicrta/gibbs.py:667-689
+* ``Gibbs.estimate_tau``     basicrta/gibbs.py:691-715
+"""
+import numpy as np
+
+from .util import confidence_interval
+
+
+def _filtered(gibbs):
+    burn = gibbs.burnin // gibbs.g
+    wcutoff = 10 / len(gibbs.times)
+    weights, rates = gibbs.mcweights[burn:], gibbs.mcrates[burn:]
+    keep = weights > wcutoff
+    return burn, wcutoff, weights, rates, keep
+
+
+def _mode(values):
+    from scipy import stats
+    return stats.mode(values).mode
+
+
+def cluster(gibbs, method='GaussianMixture', **kwargs):
+    """Cluster the retained (weight, rate) samples in log space and accumulate, per datum,
+    how often its label fell in each cluster (gibbs.py:221-273)."""
+    from sklearn import mixture
+
+    burn, wcutoff, weights, rates, keep = _filtered(gibbs)
+    lens = keep.sum(axis=1)
+    lmode = int(_mode(lens))
+    train_rows = lens == lmode
+    train = np.stack((weights[train_rows][keep[train_rows]], rates[train_rows][keep[train_rows]]), axis=1)
+    rows, comps = np.where(keep)
+    data = np.stack((weights[rows, comps], rates[rows, comps]), axis=1)
+
+    model = getattr(mixture, method)(**kwargs)
+    model.fit(np.log(train))
+    labels = model.predict(np.log(data))
+
+    indicator = gibbs.indicator[burn:] if gibbs.indicator is not None else gibbs._sample_indicator()
+    pind = np.zeros((gibbs.times.shape[0], lmode))
+    # pind[i, cluster] += 1 for every retained (row, component) whose component labels datum i
+    lut = np.full((indicator.shape[0], 256), -1, dtype=np.int16)
+    lut[rows, comps] = labels
+    for lo in range(0, indicator.shape[0], 64):                                   # bounded scratch
+        mapped = np.take_along_axis(lut[lo:lo + 64], indicator[lo:lo + 64].astype(np.int64), axis=1)
+        for c in range(lmode):
+            pind[:, c] += (mapped == c).sum(axis=0)
+    with np.errstate(invalid='ignore', divide='ignore'):
+        pind = (pind.T / pind.sum(axis=1)).T
+    gibbs.processed_results.indicator = pind
+    gibbs.processed_results.labels = labels
+    return labels
+
+
+def sort_labels(gibbs):
+    """Order clusters by mean rate, fastest first, noise clusters (no datum assigned with
+    probability >= ``_noise_cutoff``) last: basicrta/util.py:738-756."""
+    _, _, weights, rates, keep = _filtered(gibbs)
+    arates = rates[keep]
+    labels = gibbs.processed_results.labels
+    uniq = np.unique(labels)
+    imaxs = gibbs.processed_results.indicator.max(axis=0)
+    noise = np.where(imaxs < gibbs._noise_cutoff)[0]
+    means = np.array([arates[labels == i].mean() for i in uniq])
+    valid = np.delete(uniq, noise)
+    vsorts = means[valid].argsort()[::-1]
+    nsorts = means[noise].argsort()[::-1]
+    presorts = np.concatenate([valid[vsorts], noise[nsorts]]).astype(int)
+    sorts = np.array([np.where(presorts == i)[0][0] for i in uniq])
+    return sorts[labels], presorts
+
+
+def process_gibbs(gibbs, save=True):
+    """gibbs.py:275-308 without figures."""
+    burn, wcutoff, weights, rates, keep = _filtered(gibbs)
+    rows, comps = np.where(keep)
+    iteration = np.arange(gibbs.burnin, gibbs.niter + 1, gibbs.g)[rows] // gibbs.g
+    lmode = int(_mode(keep.sum(axis=1)))
+
+    cluster(gibbs, n_init=117, n_components=lmode)
+    labels, presorts = sort_labels(gibbs)
+    pr = gibbs.processed_results
+    pr.labels = labels
+    pr.indicator = pr.indicator[:, presorts]
+    pr.weights, pr.rates = weights[rows, comps], rates[rows, comps]
+    pr.ncomp, pr.residue, pr.iteration, pr.niter = lmode, gibbs.residue, iteration, gibbs.niter
+    estimate_params(gibbs)
+    if save:
+        gibbs.save()
+
+
+def estimate_params(gibbs):
+    """Mode-of-log-histogram estimates and 95 % intervals per cluster (gibbs.py:667-689)."""
+    pr = gibbs.processed_results
+    params, wb, rb = [], [], []
+    for i in range(pr.ncomp):
+        w, r = pr.weights[pr.labels == i], pr.rates[pr.labels == i]
+        row = []
+        for x in (w, r):
+            bins = np.exp(np.linspace(np.log(x.min()), np.log(x.max()), 20))
+            h = np.histogram(x, bins=bins)
+            row.append(h[1][np.argmax(h[0])])
+        params.append(row)
+        wb.append(confidence_interval(w))
+        rb.append(confidence_interval(r))
+    pr.parameters = np.array(params)
+    pr.intervals = np.array([np.array(wb), np.array(rb)])
+
+
+def estimate_tau(gibbs):
+    """[CI low, posterior mode, CI high] of tau = 1/rate of the slowest non-noise cluster
+    (gibbs.py:691-715)."""
+    pr = gibbs.processed_results
+    imaxs = pr.indicator.max(axis=0)
+    noise = np.where(imaxs < gibbs._noise_cutoff)[0]
+    inds = np.delete(np.unique(pr.labels), noise)
+    index = pr.parameters[inds, 1].argmin()
+    taus = 1 / pr.rates[pr.labels == index]
+    ci = confidence_interval(taus)
+    h = np.histogram(taus, bins=15)
+    imax = h[0].argmax()
+    return [ci[0], 0.5 * (h[1][:-1][imax] + h[1][1:][imax]), ci[1]]

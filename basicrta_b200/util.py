@@ -1,0 +1,68 @@
+"""Host-side helpers that sit next to the sampler in the reference's ``basicrta/util.py``.
+
+Only what the hot path and its pickle need is here; plotting and trajectory tools of the
+reference are out of scope.
+"""
+import numpy as np
+
+
+def get_bins(x, ts):
+    """Histogram edges ts, 2 ts, ... covering ``x`` (basicrta/util.py:653-660)."""
+    if isinstance(x, list):
+        x = np.asarray(x)
+    elif not isinstance(x, np.ndarray):
+        raise TypeError('Input should be a list or array')
+    return np.arange(1, int(x.max() // ts) + 3) * ts
+
+
+def make_surv(ahist):
+    """Empirical survival function from a histogram (basicrta/util.py:611-620): keep the
+    non-empty bins, prepend t = 0, s = 1 - cumulative fraction."""
+    counts, edges = ahist
+    keep = counts != 0
+    t = np.insert(edges[:-1][keep], 0, 0)
+    y = np.insert(np.cumsum(counts[keep]), 0, 0)
+    y = y / y[-1]
+    return t, 1 - y
+
+
+def get_s(x, ts):
+    """``t, s`` stored in the Gibbs pickle (basicrta/util.py:116-120); not used by the sampler."""
+    return make_surv(np.histogram(x, bins=get_bins(x, ts)))
+
+
+def confidence_interval(data, percentage=95):
+    """Empirical central interval (basicrta/util.py:78-91)."""
+    ds = np.sort(data)
+    perc = np.arange(1, len(ds) + 1) / len(ds)
+    lower = (100 - percentage) / 200
+    upper = (percentage + (100 - percentage) / 2) / 100
+    try:
+        lo = ds[np.where(perc <= lower)[0][-1]]
+        hi = ds[np.where(perc >= upper)[0][0]]
+    except IndexError:
+        lo, hi = ds[0], ds[-1]
+    return [lo, hi]
+
+
+def simulate_hn(n, weights, rates, seed=None, ts=None):
+    """Hyper-exponential sample (basicrta/util.py:596-608), seeded; with ``ts`` the values
+    are ceil-quantised to the trajectory grid as real contact durations are."""
+    rng = np.random.default_rng(seed)
+    n = int(n)
+    weights = np.asarray(weights, dtype=float)
+    comp = rng.choice(len(weights), size=n, p=weights / weights.sum())
+    x = rng.exponential(1.0 / np.asarray(rates, dtype=float)[comp])
+    if ts is not None:
+        x = np.maximum(np.ceil(x / ts), 1.0) * ts
+    x.sort()
+    return x
+
+
+def run_residue(residue, time, proc, ncomp, niter, cutoff):
+    """Worker shim of the reference's pool (basicrta/util.py:475-485): build a ``Gibbs`` for
+    one residue and run it.  ``proc`` selects the GPU (``proc % device_count``)."""
+    from .gibbs import Gibbs
+    x = np.array(time)
+    gib = Gibbs(x, residue, proc, ncomp=ncomp, niter=niter, cutoff=cutoff)
+    gib.run()

@@ -169,6 +169,12 @@ int brta_gibbs_run_batch(const brta_batch* batch, void* stream);
 int brta_philox_fill(uint32_t* out_dev, int64_t n, uint32_t x0, uint32_t c1, uint32_t c2,
                      uint32_t c3, uint64_t seed, void* stream);
 
+/* MUFU.EX2 throughput probe: `blocks` CTAs of 256 threads each execute 8*iters
+ * ex2.approx (plus as many FADD).  Timed by the caller with CUDA events it yields the
+ * measured peak the sampler's roofline fraction is quoted against.
+ * sink_dev: blocks*256 floats (never written in practice). */
+int brta_mufu_probe(float* sink_dev, int blocks, int iters, void* stream);
+
 /* Last error message of the calling thread ("" if none). */
 const char* brta_last_error(void);
 

@@ -1,0 +1,38 @@
+"""Developer tool: per-phase cycle breakdown of the sweep kernel (needs the -DBRTA_PHASE_TIMING build).
+
+    BRTA_LIB=basicrta_b200/libbrta_gibbs_dbg.so python tools/phase_timing.py 40 30000 1000
+"""
+import ctypes as C
+import sys
+
+import numpy as np
+
+sys.path.insert(0, '.')
+import torch  # noqa: E402
+from basicrta_b200 import _cabi  # noqa: E402
+from basicrta_b200.engine import ChainInput, get_engine  # noqa: E402
+
+n_chains, n, niter = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
+K = int(sys.argv[4]) if len(sys.argv) > 4 else 15
+rng = np.random.default_rng(1)
+chains = []
+for r in range(n_chains):
+    comp = rng.choice(3, size=n, p=[0.9, 0.09, 0.01])
+    x = rng.exponential(1.0 / np.array([5, 0.05, 0.001])[comp])
+    chains.append(ChainInput(ticks=np.maximum(np.ceil(x / 0.1), 1).astype(np.int64), ts=0.1, chain_id=r))
+eng = get_engine(0)
+db = eng.prepare(chains, K, niter, thin=100, seed=1)
+buf = torch.zeros(db.plan.grid * 8, dtype=torch.int64, device='cuda')
+lib = _cabi.load()
+assert lib.brta_debug_set_phase_buffer(C.c_void_p(buf.data_ptr())) == 0
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); eng.launch(db); e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1)
+ph = buf.cpu().numpy().reshape(-1, 8).astype(np.float64)
+ph = ph[ph.sum(1) > 0]
+names = ['sweep', 'S1 wait', 'partials+post', 'gather', 'S2', 'gamma', 'combine', 'S3']
+tot = ph.sum(1).mean()
+print(f'{ms:.2f} ms, {db.units / ms / 1e6:.1f} G units/s, grid {db.plan.grid}, teams {db.plan.team_size.min()}-{db.plan.team_size.max()}, '
+      f'slice {db.plan.slice_cap_quads} quads; cycles/iter {tot / niter:.0f}')
+for i, nme in enumerate(names):
+    print(f'  {nme:14s} {ph[:, i].mean() / niter:9.0f} cyc/iter  {100 * ph[:, i].mean() / tot:5.1f} %   (min {ph[:, i].min() / niter:.0f} max {ph[:, i].max() / niter:.0f})')
