@@ -1,0 +1,133 @@
+"""The drop-in boundary on the host: constructor / attributes / pickle layout of ``Gibbs``,
+round trips through OUR loader and through the REFERENCE's ``Gibbs.load`` + ``cluster``
+(the latter only where /root/reference exists, i.e. in the build container)."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from basicrta_b200 import postprocess
+from basicrta_b200.gibbs import Gibbs, ParallelGibbs
+from basicrta_b200.cluster import ProcessCluster
+from oracle import gibbs_oracle as O
+
+from _refstubs import have_reference, import_reference
+
+
+def _filled_gibbs(niter=3000, g=10, n=600, K=4, burnin=500):
+    """A Gibbs instance whose arrays come from the oracle (test-only; the product has no CPU sampler)."""
+    times = O.synth_times(n, [0.7, 0.3], [3.0, 0.05], seed=3)
+    gb = Gibbs(times, 'W313', 2, ncomp=K, niter=niter, cutoff=7.0)
+    gb.g, gb.burnin = g, burnin
+    gb._prepare()
+    out = O.run_reference_order(times, K, niter, np.random.default_rng(5), g=g)
+    gb.mcweights, gb.mcrates, gb.indicator = out['mcweights'], out['mcrates'], out['indicator']
+    return gb
+
+
+def test_constructor_defaults_and_ts():
+    gb = Gibbs()
+    assert (gb.times, gb.residue, gb.loc, gb.ncomp, gb.niter, gb.cutoff) == (None, None, 0, 15, 110000, None)
+    assert (gb.g, gb.burnin, gb._noise_cutoff, gb.ts) == (100, 10000, 0.4, None)
+    assert gb.keys == {'times', 'residue', 'loc', 'ncomp', 'niter', 'g', 'burnin', 'processed_results', 'ts',
+                       'mcweights', 'mcrates', 't', 's', 'cutoff', 'indicator'}
+    gb = Gibbs(np.array([0.3, 0.1, 0.1, 0.5]), 'X1')
+    assert np.isclose(gb.ts, 0.2) and gb['residue'] == 'X1'
+    gb = Gibbs(np.array([0.4, 0.4]), 'X1')                 # no non-zero gap: falls back to min (gibbs.py:150-151)
+    assert gb.ts == 0.4
+
+
+def test_save_load_roundtrip_and_bak_rotation(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    gb = _filled_gibbs()
+    with pytest.raises(OSError):
+        gb.save()                                           # directory missing (gibbs.py:348-349)
+    os.makedirs('basicrta-7.0/W313')
+    gb.save()
+    gb.save()
+    assert os.path.exists('basicrta-7.0/W313/gibbs_3000.pkl.bak')
+    back = Gibbs.load('basicrta-7.0/W313/gibbs_3000.pkl')
+    for attr in ('times', 'mcweights', 'mcrates', 'indicator', 't', 's', 'whypers', 'rhypers'):
+        assert np.array_equal(getattr(back, attr), getattr(gb, attr)), attr
+    assert (back.residue, back.ncomp, back.niter, back.g, back.burnin, back.cutoff) == ('W313', 4, 3000, 10, 500, 7.0)
+    raw = pickle.load(open('basicrta-7.0/W313/gibbs_3000.pkl', 'rb'))
+    assert raw.indicator.dtype == np.uint8 and raw.indicator.flags['C_CONTIGUOUS']
+    assert raw.mcweights.dtype == np.float64 and raw.mcweights.shape == (300, 4)
+
+
+def test_postprocess_recovers_components(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    gb = _filled_gibbs()
+    os.makedirs('basicrta-7.0/W313')
+    gb.process_gibbs()
+    pr = gb.processed_results
+    assert pr.ncomp == 2 and pr.indicator.shape == (600, 2)
+    assert np.allclose(pr.indicator.sum(axis=1), 1.0)
+    assert 2.0 < pr.parameters[0, 1] < 4.5 and 0.03 < pr.parameters[1, 1] < 0.08     # sorted fastest first
+    lo, tau, hi = gb.estimate_tau()
+    assert lo < tau < hi and 12 < tau < 35                  # 1 / 0.05 = 20 ns
+
+
+@pytest.mark.skipif(not have_reference(), reason='/root/reference not present (GPU box)')
+def test_reference_loads_our_pickle_and_clusters_identically(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    gb = _filled_gibbs()
+    os.makedirs('basicrta-7.0/W313')
+    gb.save()
+    ref_gibbs, _ = import_reference()
+    rg = ref_gibbs.Gibbs().load('basicrta-7.0/W313/gibbs_3000.pkl')
+    assert type(rg).__module__ == 'basicrta.gibbs'
+    for attr in ('times', 'mcweights', 'mcrates', 'indicator', 't', 's', 'whypers', 'rhypers'):
+        assert np.array_equal(getattr(rg, attr), getattr(gb, attr)), attr
+    rg.cluster(n_init=2, n_components=2, random_state=0)
+    postprocess.cluster(gb, n_init=2, n_components=2, random_state=0)
+    assert np.array_equal(rg.processed_results.labels, gb.processed_results.labels)
+    assert np.allclose(rg.processed_results.indicator, gb.processed_results.indicator, equal_nan=True)
+    # and our loader reads a pickle written by the reference class
+    ref_gibbs.rng = np.random.default_rng(1)
+    ref_gibbs.tqdm = lambda it, **kw: it
+    r2 = ref_gibbs.Gibbs(gb.times, 'A1', 0, ncomp=3, niter=50, cutoff=7.0)
+    r2.g = 5
+    r2.run()
+    ours = Gibbs.load('basicrta-7.0/A1/gibbs_50.pkl')
+    assert np.array_equal(ours.mcrates, r2.mcrates) and ours.indicator.shape == (10, 600)
+
+
+def test_parallel_gibbs_surface(tmp_path):
+    pg = ParallelGibbs('some/dir/contacts_7.0.pkl', nproc=4, ncomp=7, niter=1000)
+    assert (pg.cutoff, pg.nproc, pg.ncomp, pg.niter) == (7.0, 4, 7, 1000)
+    assert issubclass(ProcessCluster, ParallelGibbs)
+    # residue slicing: column 0 = protein resid, column 3 = duration (contacts.py:227-229)
+    rng = np.random.default_rng(0)
+    contacts = np.zeros((1000, 4))
+    contacts[:, 0] = rng.integers(10, 15, 1000)
+    contacts[:, 3] = rng.integers(1, 50, 1000) * 0.1
+    path = tmp_path / 'contacts_7.0.pkl'
+    with open(path, 'wb') as f:
+        pickle.dump(contacts, f)
+    pg = ParallelGibbs(str(path), nproc=1)
+    resids, names, times = pg._load(None)
+    assert list(resids) == [10, 11, 12, 13, 14] and names[0] == 'X10'
+    for r, t in zip(resids, times):
+        assert np.array_equal(np.sort(t), np.sort(contacts[contacts[:, 0] == r][:, 3]))
+    resids, names, times = pg._load(12)
+    assert list(resids) == [12] and len(times) == 1
+
+
+def test_compat_shim_exposes_reference_import_paths():
+    import sys
+    from basicrta_b200 import compat
+    saved = {k: v for k, v in sys.modules.items() if k == 'basicrta' or k.startswith('basicrta.')}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        compat.install(force=True)
+        from basicrta.gibbs import Gibbs as G2, ParallelGibbs as P2
+        from basicrta.util import run_residue
+        from basicrta.cluster import ProcessCluster as C2
+        assert G2 is Gibbs and P2 is ParallelGibbs and C2 is ProcessCluster and callable(run_residue)
+    finally:
+        for k in [k for k in sys.modules if k == 'basicrta' or k.startswith('basicrta.')]:
+            del sys.modules[k]
+        sys.modules.update(saved)

@@ -1,0 +1,81 @@
+"""The C-ABI library loads and exports every symbol include/basicrta_b200.h declares (no
+compute calls: this runs without a GPU), and the ctypes mirrors match the header."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from basicrta_b200 import _cabi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = open(os.path.join(ROOT, 'include', 'basicrta_b200.h')).read()
+
+
+def _declared_functions():
+    body = HEADER[HEADER.index('typedef struct brta_batch'):]
+    return sorted(set(re.findall(r'^\s*(?:const\s+)?(?:int|char\*?)\s*\*?\s*(brta_\w+)\s*\(', body, flags=re.M)))
+
+
+def test_library_exports_every_declared_symbol():
+    _cabi.build()
+    lib = _cabi.load()
+    declared = _declared_functions()
+    assert set(declared) == set(_cabi.EXPORTS), (declared, _cabi.EXPORTS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.brta_abi_version() == int(re.search(r'#define BRTA_ABI_VERSION (\d+)', HEADER).group(1))
+    assert lib.brta_last_error() == b''
+
+
+def _struct_fields(name):
+    m = re.search(r'typedef struct %s \{(.*?)\} %s;' % (name, name), HEADER, flags=re.S)
+    body = re.sub(r'/\*.*?\*/', '', m.group(1), flags=re.S)
+    fields = []
+    for decl in body.split(';'):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names = decl.split(',')
+        fields.append(re.findall(r'(\w+)\s*$', names[0])[0])
+        for extra in names[1:]:
+            fields.append(extra.strip().lstrip('*').strip())
+    return fields
+
+
+@pytest.mark.parametrize('cname,cls', [('brta_caps', _cabi.Caps), ('brta_launch_info', _cabi.LaunchInfo),
+                                       ('brta_task', _cabi.Task), ('brta_batch', _cabi.Batch)])
+def test_ctypes_mirror_matches_header(cname, cls):
+    assert _struct_fields(cname) == [f[0] for f in cls._fields_]
+
+
+def test_constants_match_header():
+    def macro(name):
+        return re.search(r'#define\s+%s\s+\(?([0-9a-fx]+)u?' % name, HEADER).group(1)
+    assert int(macro('BRTA_THREADS')) == _cabi.THREADS
+    assert int(macro('BRTA_MAX_NCOMP')) == _cabi.MAX_NCOMP
+    assert int(macro('BRTA_MAILBOX_MAX_TEAM')) == _cabi.MAILBOX_MAX_TEAM
+    for flag in ('EXACT', 'INJECT_COEF', 'INJECT_U', 'TRACE'):
+        assert int(macro('BRTA_FLAG_' + flag)) == getattr(_cabi, 'FLAG_' + flag)
+    from basicrta_b200.plan import TASK_DTYPE
+    assert TASK_DTYPE.itemsize == C.sizeof(_cabi.Task)
+    assert list(TASK_DTYPE.names) == [f[0] for f in _cabi.Task._fields_]
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    lib = _cabi.load()
+    assert lib.brta_gibbs_run_batch(None, None) == -1                     # BRTA_E_NULL
+    assert b'NULL' in lib.brta_last_error()
+    b = _cabi.Batch()
+    b.ncomp = 99
+    assert lib.brta_gibbs_run_batch(C.byref(b), None) == -2               # BRTA_E_NCOMP
+    assert lib.brta_query(0, None) == -1
+
+
+def test_product_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    from basicrta_b200.engine import GibbsEngine
+    with pytest.raises(_cabi.BrtaError):
+        GibbsEngine(0)

@@ -1,0 +1,155 @@
+"""The public API on the GPU: Gibbs.run / _sample_indicator / ParallelGibbs.run, edge cases."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+from basicrta_b200 import _cabi
+from basicrta_b200.engine import ChainInput
+from basicrta_b200.gibbs import Gibbs, ParallelGibbs, run_batch
+from oracle import gibbs_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gibbs_run_writes_reference_layout(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    times = O.synth_times(4000, [0.8, 0.2], [4.0, 0.05], seed=2)
+    g = Gibbs(times, 'W313', 0, ncomp=5, niter=5000, cutoff=7.0)
+    g.g, g.seed = 50, 3                                      # attribute override after construction
+    g.run()
+    assert os.path.exists('basicrta-7.0/W313/gibbs_5000.pkl')
+    back = Gibbs.load('basicrta-7.0/W313/gibbs_5000.pkl')
+    assert back.mcweights.shape == (100, 5) and back.indicator.shape == (100, 4000)
+    assert back.indicator.dtype == np.uint8 and back.mcrates.dtype == np.float64
+    assert np.allclose(back.mcweights.sum(1), 1, atol=1e-5)
+    w, r = back.mcweights[40:], back.mcrates[40:]
+    assert abs(r[w > 0.5].mean() / 3.2 - 1) < 0.15           # 4 /ns on a 0.1 ns ceil grid reads ~3.2
+    # same seed -> same chain; different seed -> different chain
+    g2 = Gibbs(times, 'W313', 0, ncomp=5, niter=5000, cutoff=7.0)
+    g2.g, g2.seed = 50, 3
+    g2._prepare()
+    run_batch([g2], prepared=True)
+    assert np.array_equal(g2.mcrates, back.mcrates) and np.array_equal(g2.indicator, back.indicator)
+    g2.seed = 4
+    run_batch([g2], prepared=True)
+    assert not np.array_equal(g2.mcrates, back.mcrates)
+
+
+def test_hyperparameters_are_read_at_run_time():
+    times = O.synth_times(2000, [1.0], [1.0], seed=1)
+    g = Gibbs(times, 'X1', 0, ncomp=3, niter=2000, cutoff=1.0)
+    g.seed = 1
+    g._prepare()
+    g.rhypers = np.ones((3, 2)) * [1.0, 3.0e6]               # a crushing prior on the rates
+    run_batch([g], prepared=True)
+    assert g.mcrates[10:].max() < 0.01
+
+
+def test_sample_indicator_redraws_labels():
+    times = O.synth_times(3000, [0.7, 0.3], [3.0, 0.05], seed=4)
+    g = Gibbs(times, 'X2', 0, ncomp=4, niter=2000, cutoff=1.0)
+    g.g, g.burnin, g.seed = 20, 400, 5
+    g._prepare()
+    run_batch([g], prepared=True)
+    kept = g.indicator.copy()
+    g.indicator = None
+    tail = g._sample_indicator()
+    assert g.indicator.shape == kept.shape and tail.shape == (80, 3000)
+    # new draws from the stored post-update parameters: same label distribution, not the same labels
+    f_old = np.bincount(kept[50:].ravel(), minlength=4) / kept[50:].size
+    f_new = np.bincount(g.indicator[50:].ravel(), minlength=4) / kept[50:].size
+    assert np.abs(np.sort(f_old) - np.sort(f_new)).max() < 0.01
+
+
+def test_parallel_gibbs_runs_residues(tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.default_rng(0)
+    rows = []
+    for resid, n in ((101, 900), (102, 3001), (105, 37)):
+        rows.append(np.stack([np.full(n, resid), rng.integers(1, 30, n), rng.random(n),
+                              np.ceil(rng.exponential(2.0, n) / 0.1) * 0.1], axis=1))
+    contacts = np.concatenate(rows)
+    rng.shuffle(contacts)
+    with open('contacts_7.0.pkl', 'wb') as f:
+        pickle.dump(contacts, f)
+    out = ParallelGibbs('contacts_7.0.pkl', nproc=1, ncomp=4, niter=1000).run()
+    assert sorted(g.residue for g in out) == ['X101', 'X102', 'X105']
+    for g in out:
+        back = Gibbs.load(f'basicrta-7.0/{g.residue}/gibbs_1000.pkl')
+        assert back.indicator.shape == (10, len(g.times)) and back.mcrates.shape == (10, 4)
+        assert np.all(back.mcrates > 0) and back.indicator.max() < 4
+    only = ParallelGibbs('contacts_7.0.pkl', nproc=1, ncomp=4, niter=200).run(run_resids=102)
+    assert [g.residue for g in only] == ['X102']
+
+
+@pytest.mark.parametrize('n', [1, 2, 3, 5, 127, 129, 513])
+def test_ragged_sizes_exact(engine, n):
+    """N not a multiple of 4 / smaller than a CTA: padding must never be counted."""
+    K, niter = 3, 6
+    times = O.synth_times(n, [0.6, 0.4], [2.0, 0.1], seed=n)
+    ts = 0.1
+    ticks = O.to_ticks(times, ts)
+    ref = O.run_teacher_forced(ticks, ts, K, niter, seed=1, chain_id=n, rng=np.random.default_rng(n), g=1)
+    flags = _cabi.FLAG_EXACT | _cabi.FLAG_INJECT_COEF | _cabi.FLAG_TRACE
+    got = engine.run([ChainInput(ticks=ticks, ts=ts, chain_id=n)], K, niter, thin=1, seed=1, flags=flags,
+                     inject={'coef_c': [ref['coef_c']], 'coef_a': [ref['coef_a']]})[0]
+    assert np.array_equal(got.trace_nk, ref['nk']) and got.trace_nk.sum(axis=1).tolist() == [n] * niter
+    assert np.array_equal(got.trace_tk, ref['tk']) and np.array_equal(got.indicator, ref['indicator'])
+
+
+def test_uint32_ticks_and_large_values(engine):
+    """Ticks >= 65536 take the uint32 path; sums stay exact."""
+    K, niter = 4, 8
+    rng = np.random.default_rng(3)
+    ticks = np.concatenate([rng.integers(1, 50, 3000), rng.integers(70000, 4000000, 40)]).astype(np.int64)
+    ref = O.run_teacher_forced(ticks, 0.01, K, niter, seed=2, chain_id=1, rng=np.random.default_rng(1), g=2)
+    flags = _cabi.FLAG_EXACT | _cabi.FLAG_INJECT_COEF | _cabi.FLAG_TRACE
+    got = engine.run([ChainInput(ticks=ticks, ts=0.01, chain_id=1)], K, niter, thin=2, seed=2, flags=flags,
+                     inject={'coef_c': [ref['coef_c']], 'coef_a': [ref['coef_a']]})[0]
+    assert np.array_equal(got.trace_nk, ref['nk']) and np.array_equal(got.trace_tk, ref['tk'])
+    assert np.array_equal(got.indicator, ref['indicator'])
+
+
+def test_stress_k30_four_decades(engine):
+    """Config C5 in miniature: K = 30 (initial rates down to 5e-29, gibbs.py:186), true rates over
+    4 decades.  The reference's linear-space likelihood can produce NaN here; the log-space kernel
+    must finish with status 0 and find the fast and the slow end."""
+    n = 20000
+    times = O.synth_times(n, [0.6, 0.25, 0.1, 0.04, 0.01], [10, 1, 0.1, 0.01, 0.001], seed=5000)
+    ticks = O.to_ticks(times, 0.1)
+    res = engine.run([ChainInput(ticks=ticks, ts=0.1, chain_id=7)], 30, 20000, thin=100, seed=9)[0]
+    assert res.status == 0 and np.isfinite(res.mcrates).all() and np.isfinite(res.mcweights).all()
+    w, r = res.mcweights[100:], res.mcrates[100:]
+    sig = w > 10.0 / n
+    assert r[sig].max() > 2.0 and r[sig].min() < 0.003
+    assert res.indicator.max() < 30
+
+
+def test_large_team_atomics_path_exact(engine):
+    """A chain wide enough for a team > BRTA_MAILBOX_MAX_TEAM uses the L2-atomics exchange."""
+    K, niter = 6, 6
+    times = O.synth_times(40000, [0.9, 0.1], [5, 0.05], seed=11)
+    ticks = O.to_ticks(times, 0.1)
+    ref = O.run_teacher_forced(ticks, 0.1, K, niter, seed=4, chain_id=3, rng=np.random.default_rng(2), g=3)
+    flags = _cabi.FLAG_EXACT | _cabi.FLAG_INJECT_COEF | _cabi.FLAG_TRACE
+    db = engine.prepare([ChainInput(ticks=ticks, ts=0.1, chain_id=3)], K, niter, thin=3, seed=4, flags=flags,
+                        inject={'coef_c': [ref['coef_c']], 'coef_a': [ref['coef_a']]})
+    assert db.plan.team_size[0] > _cabi.MAILBOX_MAX_TEAM
+    engine.launch(db)
+    got = engine.fetch(db)[0]
+    assert np.array_equal(got.trace_nk, ref['nk']) and np.array_equal(got.trace_tk, ref['tk'])
+    assert np.array_equal(got.indicator, ref['indicator'])
+
+
+def test_argument_validation(engine):
+    with pytest.raises(ValueError):
+        engine.prepare([ChainInput(ticks=np.array([1, 2, 3]), ts=0.1)], 33, 10)
+    with pytest.raises(ValueError):
+        engine.prepare([ChainInput(ticks=np.array([], dtype=np.int64), ts=0.1)], 3, 10)
+    with pytest.raises(ValueError):
+        engine.prepare([ChainInput(ticks=np.array([1 << 23]), ts=0.1)], 3, 10)
+    from basicrta_b200.engine import times_to_ticks
+    with pytest.raises(ValueError):
+        times_to_ticks(np.array([0.1, 0.25, 0.3]), 0.1)      # not on the grid

@@ -1,0 +1,73 @@
+"""Host schedule: every quad of every chain is owned by exactly one CTA, team members share a
+wave, no CTA holds two tasks of one wave, slices fit the capacity."""
+import numpy as np
+import pytest
+
+from basicrta_b200.plan import MIN_SLICE_QUADS, build_plan, shard_chains
+
+
+def _check(plan, n_quads, grid, cap):
+    n_quads = np.asarray(n_quads)
+    R = len(n_quads)
+    covered = [np.zeros(q, dtype=np.int32) for q in n_quads]
+    ranks = [set() for _ in range(R)]
+    for b in range(grid):
+        waves = []
+        for t in plan.tasks_of_cta(b):
+            r = int(t['chain'])
+            covered[r][t['quad_begin']:t['quad_begin'] + t['quad_count']] += 1
+            assert t['team_size'] == plan.team_size[r]
+            assert 0 <= t['team_rank'] < t['team_size']
+            assert t['team_rank'] not in ranks[r]
+            ranks[r].add(int(t['team_rank']))
+            assert t['order'] == plan.wave_of_chain[r]
+            assert 1 <= t['quad_count'] <= cap
+            waves.append(int(t['order']))
+        assert waves == sorted(set(waves)), 'a CTA walks its waves in ascending order, one task per wave'
+    for r in range(R):
+        assert np.all(covered[r] == 1)
+        assert ranks[r] == set(range(int(plan.team_size[r])))
+    assert plan.cta_task_begin[0] == 0 and plan.cta_task_begin[-1] == len(plan.tasks)
+    assert plan.slice_cap_quads == plan.tasks['quad_count'].max()
+
+
+@pytest.mark.parametrize('seed,R,grid,cap', [(0, 400, 592, 3000), (1, 50, 592, 3000), (2, 2000, 296, 7000),
+                                            (3, 1, 592, 3000), (4, 7, 8, 100000), (5, 1000, 16, 500)])
+def test_plan_partitions_every_chain(seed, R, grid, cap):
+    rng = np.random.default_rng(seed)
+    n = np.round(10 ** rng.uniform(2, 5, R)).astype(np.int64)
+    q = np.minimum((n + 3) // 4, cap * grid // max(1, R) + 50)
+    plan = build_plan(q, grid, cap)
+    _check(plan, q, grid, cap)
+
+
+def test_plan_c2_efficiency_and_giant_chain():
+    rng = np.random.default_rng(0)
+    q = (np.round(10 ** rng.uniform(4, 5, 400)).astype(np.int64) + 3) // 4
+    plan = build_plan(q, 592, 3000)
+    assert plan.est_efficiency > 0.85
+    giant = build_plan([250000], 592, 3000)                  # config C4 on one GPU
+    assert giant.team_size[0] == 592 and giant.n_waves == 1
+    _check(giant, [250000], 592, 3000)
+    tiny = build_plan([5], 592, 3000)                        # N = 20: one CTA, no exchange
+    assert tiny.team_size[0] == 1
+    small = build_plan([1250], 592, 3000)                    # config C1: slices stay >= MIN_SLICE_QUADS
+    assert small.tasks['quad_count'].min() >= MIN_SLICE_QUADS - 1
+
+
+def test_plan_rejects_bad_input():
+    with pytest.raises(ValueError):
+        build_plan([], 8, 100)
+    with pytest.raises(ValueError):
+        build_plan([0, 3], 8, 100)
+    with pytest.raises(ValueError):
+        build_plan([10 ** 6], 4, 100)                        # does not fit 4 CTAs x 100 quads
+
+
+def test_shard_chains_lpt():
+    costs = np.array([100, 90, 50, 40, 30, 20, 10, 5])
+    shards = shard_chains(costs, 3)
+    assert sorted(np.concatenate(shards).tolist()) == list(range(8))
+    loads = [costs[s].sum() for s in shards]
+    assert max(loads) - min(loads) <= 20
+    assert all(len(s) == 0 for s in shard_chains([], 2))
