@@ -120,7 +120,7 @@ class Gibbs(object):
                       inject={'coef_c': [np.stack([c for c, _ in coef])],
                               'coef_a': [np.stack([a for _, a in coef])]})[0]
         _raise_on_status(self.residue, res.status)
-        self.indicator = res.indicator
+        self.indicator = np.ascontiguousarray(res.indicator[:rows])   # (niter+1)//1 rows are allocated, `rows` filled
         return self.indicator[self.burnin // self.g:]
 
     # ---- persistence (gibbs.py:336-381) ---------------------------------------------------
