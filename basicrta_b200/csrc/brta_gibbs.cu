@@ -14,10 +14,12 @@
 //   * sufficient statistics (n_k, sum of ticks) are exact integers (gibbs.py:203-207):
 //     shared-memory atomics for every label except the currently dominant one, whose
 //     statistics follow by subtraction from the slice totals;
-//   * team members add their partials into the chain's exchange buffer in L2
-//     (red.global.add) and rendezvous on a monotonic arrive counter; every member then
-//     draws the same Dirichlet / Gamma update (gibbs.py:210-211) from the same Philox
-//     key with one warp (lane k = component k), so no broadcast is needed;
+//   * team members post their partials into the chain's tagged mailboxes in L2 (one
+//     64-bit word per value, valid once it carries the iteration number -- no fence, no
+//     flag) and every warp gathers a share of them; teams wider than 32 CTAs fall back to
+//     L2 atomics + a monotonic arrive counter.  Every member then draws the same
+//     Dirichlet / Gamma update (gibbs.py:210-211) from the same Philox key (lane k =
+//     component k, one Marsaglia-Tsang trial per warp in parallel), so no broadcast is needed;
 //   * every `thin`-th iteration the labels (4 per 32-bit store) and, from team rank 0,
 //     the post-update weights/rates are written (gibbs.py:214-217).
 //
@@ -36,6 +38,7 @@ namespace brta {
 
 constexpr int THREADS = BRTA_THREADS;
 constexpr int WARPS = THREADS / 32;
+constexpr int NTRIALS = WARPS / 2;                        // Marsaglia-Tsang trials run in parallel per draw
 
 // exchange workspace of one chain (BRTA_EXCH_STRIDE bytes):
 //   sum[3][32] u64 @ 0, cnt[3][32] u32 @ 768, arrive u32 @ 1152
@@ -99,7 +102,7 @@ __device__ __forceinline__ void search_level(const float (&cum)[K], float thr, b
     if constexpr (LVL <= LEVELS) {
         const float pv = pivot_mux<K, P, LVL - 1, (1 << (LEVELS - LVL)) - 1, 1 << (LEVELS - LVL + 1)>(cum, p);
         p[LVL - 1] = pv <= thr;
-        c += p[LVL - 1] ? (1 << (LEVELS - LVL)) : 0;
+        if (p[LVL - 1]) c |= (1 << (LEVELS - LVL));
         search_level<K, P, LEVELS, LVL + 1>(cum, thr, p, c);
     }
 }
@@ -123,7 +126,7 @@ __device__ __forceinline__ int count_le(const float (&cum)[K], float thr)
 template <int K, int D, bool EXACT>
 __device__ __forceinline__ void draw_labels(const float (&tick)[D], const float (&f12)[D],
                                             const float2* __restrict__ s_coef, int kmax,
-                                            int (&lab)[D], bool& bad)
+                                            int (&lab)[D])
 {
     float l[D][K];
     float m[D];
@@ -160,9 +163,14 @@ __device__ __forceinline__ void draw_labels(const float (&tick)[D], const float 
         // bits as the oracle's float32 product
         const float thr = __fmaf_rn(f12[d], cum[d], -cum[d]);
         lab[d] = min(count_le<K>(l[d], thr), kmax);
-        bad |= !(cum[d] > 0.5f);                           // the max term contributes 1; catches NaN
     }
 }
+
+// data of one quad processed together by a thread (register pressure vs ILP)
+#ifndef BRTA_D_SMALLK
+#define BRTA_D_SMALLK 4
+#endif
+__host__ __device__ constexpr int data_in_flight(int k) { return k <= 16 ? BRTA_D_SMALLK : 2; }
 
 // Kernel parameters: the caller's batch plus the Philox key schedule, both in the constant bank.
 struct SweepParams {
@@ -171,7 +179,7 @@ struct SweepParams {
 };
 
 // Shared-memory reductions of one datum: n_k += 1 and, 128 bytes further, the tick
-// accumulator, addressed in the shared window (no generic->shared arithmetic in the loop).
+// accumulator, addressed in the shared window.
 __device__ __forceinline__ void red_shared_stats(uint32_t cnt_addr, uint32_t tick_bits)
 {
     asm volatile("red.shared.add.u32 [%0], 1;\n\t"
@@ -185,12 +193,17 @@ __device__ __forceinline__ void red_shared_stats(uint32_t cnt_addr, uint32_t tic
 constexpr uint32_t TICK_BIAS = 0x4B000000u;
 
 // One quad (4 data) of the sweep: labels, statistics, optional label store.
+//
+// Statistics: shared-memory atomics for every label except the currently dominant one
+// (`dom`, the most populated component of the previous iteration), whose statistics follow
+// by subtraction from the slice totals -- exact integer arithmetic, so any choice of `dom`
+// gives the same result; skipping it removes most of the same-address contention.
 template <int K, bool EXACT, bool SAVE>
 __device__ __forceinline__ void sweep_quad(const float4 tk, const float4 f12, const float2* __restrict__ s_coef,
                                            int kmax, int dom, int i0, int n_data, bool partial,
-                                           uint32_t stat_addr, uint8_t* ind_row, bool& bad)
+                                           uint32_t stat_addr, uint8_t* ind_row)
 {
-    constexpr int D = (K <= 16) ? 4 : 2;                   // data in flight per thread
+    constexpr int D = data_in_flight(K);
     const float tks[4] = {tk.x, tk.y, tk.z, tk.w};
     const float fs[4] = {f12.x, f12.y, f12.z, f12.w};      // uniforms as floats in [1,2)
     int labs[4];
@@ -200,7 +213,7 @@ __device__ __forceinline__ void sweep_quad(const float4 tk, const float4 f12, co
         int ld[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) { td[d] = tks[h + d]; fd[d] = fs[h + d]; }
-        draw_labels<K, D, EXACT>(td, fd, s_coef, kmax, ld, bad);
+        draw_labels<K, D, EXACT>(td, fd, s_coef, kmax, ld);
 #pragma unroll
         for (int d = 0; d < D; ++d) labs[h + d] = ld[d];
     }
@@ -211,7 +224,7 @@ __device__ __forceinline__ void sweep_quad(const float4 tk, const float4 f12, co
     }
 #pragma unroll
     for (int d = 0; d < 4; ++d)
-        if (labs[d] != dom)                                // ~10 % of the lanes: ATOMS cost scales with them
+        if (labs[d] != dom)                                // ATOMS cost scales with the active lanes
             red_shared_stats(stat_addr + 4u * (uint32_t)labs[d], __float_as_uint(tks[d] + 8388608.0f));
     if (SAVE) {                                            // 1 iteration in `thin`: dense [S,N] bytes
 #pragma unroll
@@ -225,7 +238,7 @@ __device__ __forceinline__ void sweep_slice(const float4* __restrict__ s_tick4, 
                                             int nq, int qb, int n_data, int kmax, int dom, uint32_t j,
                                             uint32_t chain_id, const RoundKeys& rk,
                                             const float4* __restrict__ u_row, uint32_t stat_addr,
-                                            uint8_t* ind_row, bool& bad)
+                                            uint8_t* ind_row)
 {
     // at most one quad of the whole chain is partial; find out once whether it is in this slice
     const int tail_q = ((n_data & 3) != 0) ? (n_data >> 2) - qb : -1;
@@ -240,11 +253,11 @@ __device__ __forceinline__ void sweep_slice(const float4* __restrict__ s_tick4, 
             f12 = make_float4(word_to_12(w.x), word_to_12(w.y), word_to_12(w.z), word_to_12(w.w));
         }
         sweep_quad<K, EXACT, SAVE>(tk, f12, s_coef, kmax, dom, (qb + q) * 4, n_data, q == tail_q,
-                                   stat_addr, ind_row, bad);
+                                   stat_addr, ind_row);
     }
 }
 
-// Developer-only phase timing (-DBRTA_PHASE_TIMING builds libbrta_gibbs_dbg.so): thread 0 of
+// Developer-only phase timing (-DBRTA_PHASE_TIMING builds a debug library): thread 0 of
 // every CTA accumulates clock64 deltas per phase into g_phase[blockIdx.x][8].
 #ifdef BRTA_PHASE_TIMING
 __device__ unsigned long long* g_phase = nullptr;
@@ -257,6 +270,11 @@ __device__ unsigned long long* g_phase = nullptr;
 #define PHASE_FLUSH
 #endif
 
+__device__ __forceinline__ bool coef_ok(float2 ca)
+{
+    return (ca.x == ca.x) && (ca.x < INFINITY) && (ca.y >= 0.0f) && (ca.y < INFINITY);
+}
+
 __device__ __forceinline__ void named_barrier_sync(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
@@ -264,7 +282,13 @@ __device__ __forceinline__ void named_barrier_sync(int id, int nthreads)
 
 // co-resident CTAs per SM the register budget is capped for: the serial section of one
 // CTA (exchange + posterior draw) is hidden by the sweeps of the others
-constexpr int min_ctas(int k) { return k <= 16 ? 512 / THREADS : 384 / THREADS; }
+#ifndef BRTA_MIN_CTAS_SMALLK
+#define BRTA_MIN_CTAS_SMALLK (512 / THREADS)
+#endif
+#ifndef BRTA_MIN_CTAS_LARGEK
+#define BRTA_MIN_CTAS_LARGEK (384 / THREADS)
+#endif
+constexpr int min_ctas(int k) { return k <= 16 ? BRTA_MIN_CTAS_SMALLK : BRTA_MIN_CTAS_LARGEK; }
 
 template <int K, bool EXACT>
 __global__ void __launch_bounds__(THREADS, min_ctas(K))
@@ -280,13 +304,14 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
     __shared__ __align__(16) unsigned s_stat[64];
     unsigned* const s_cnt = s_stat;
     unsigned* const s_sum = s_stat + 32;
-    const uint32_t stat_addr = (uint32_t)__cvta_generic_to_shared(s_stat);
-    __shared__ unsigned s_tot_c[WARPS][32];                // team totals, one row per gathering warp
-    __shared__ unsigned long long s_tot_s[WARPS][32];
-    __shared__ float s_rate[32], s_l2r[32];                // warp 1 -> warp 0: rate, log2(rate)
+    uint32_t stat_addr = (uint32_t)__cvta_generic_to_shared(s_stat);
     __shared__ unsigned long long s_red_t[WARPS];
     __shared__ unsigned s_red_n[WARPS];
     __shared__ int s_dom;
+    __shared__ unsigned s_tot_c[WARPS][32];                // team totals, one row per gathering warp
+    __shared__ unsigned long long s_tot_s[WARPS][32];
+    __shared__ float s_try_g[2][NTRIALS][32];              // parallel Marsaglia-Tsang trials: d*v or NaN
+    __shared__ float s_try_b[2][NTRIALS][32];              //   and log2 of the shape < 1 boost uniform
     __shared__ unsigned s_bad;
 
     const int tid = threadIdx.x;
@@ -358,7 +383,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
         if (tid == 0) { s_dom = 0; s_bad = 0; }
         __syncthreads();
 
-        // slice totals (warp 0) and per-component priors (warp 0: Dirichlet, warp 1: Gamma)
+        // slice totals (warp 0) and per-component priors, lane = component
         unsigned slice_n = 0;
         unsigned long long slice_t = 0;
         float wh = 0.0f, rh_a = 1.0f, rh_b = 1.0f;
@@ -366,7 +391,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
 #pragma unroll
             for (int w = 0; w < WARPS; ++w) { slice_n += s_red_n[w]; slice_t += s_red_t[w]; }
         }
-        if (warp < 2 && lane < kreal) {
+        if (lane < kreal) {
             wh = b.whyper[(size_t)r * kreal + lane];
             rh_a = b.rhyper[((size_t)r * kreal + lane) * 2 + 0];
             rh_b = b.rhyper[((size_t)r * kreal + lane) * 2 + 1];
@@ -385,7 +410,9 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
             if (inject_coef) {
                 if (tid < kreal) {
                     const size_t o = ((size_t)r * niter + (j - 1)) * kreal + tid;
-                    s_coef[tid] = make_float2(b.inj_c[o], b.inj_a[o]);
+                    const float2 ca = make_float2(b.inj_c[o], b.inj_a[o]);
+                    bad |= !coef_ok(ca);
+                    s_coef[tid] = ca;
                 }
                 __syncthreads();
             }
@@ -393,15 +420,16 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
             const int row = j / thin - 1;
             const float4* const u_row = inject_u
                 ? reinterpret_cast<const float4*>(inj_u_base + (size_t)(j - 1) * u_pitch) : nullptr;
+
             const int dom = s_dom;
 
             // ---- indicator draws + sufficient statistics (gibbs.py:196-207) -------------
             if (save)
                 sweep_slice<K, EXACT, true>(s_tick4, s_coef, nq, qb, n_data, kreal - 1, dom, (uint32_t)j, chain_id,
-                                            prm.rk, u_row, stat_addr, ind_base + (size_t)row * ind_stride, bad);
+                                            prm.rk, u_row, stat_addr, ind_base + (size_t)row * ind_stride);
             else
                 sweep_slice<K, EXACT, false>(s_tick4, s_coef, nq, qb, n_data, kreal - 1, dom, (uint32_t)j, chain_id,
-                                             prm.rk, u_row, stat_addr, nullptr, bad);
+                                             prm.rk, u_row, stat_addr, nullptr);
             PHASE_MARK(0);                                 // sweep
             __syncthreads();
             PHASE_MARK(1);                                 // wait for the CTA's slowest warp
@@ -448,6 +476,12 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
                 }
             }
             PHASE_MARK(2);                                 // partials + post
+            // shape-independent half of this warp's Marsaglia-Tsang trial, overlapped with the exchange
+            const int draw_type = warp & 1;                // 0: Dirichlet gamma (weights), 1: rate gamma
+            TrialRandoms rnd = {};
+            if (!inject_coef)
+                rnd = trial_randoms(philox4x32_10_rk((uint32_t)(warp >> 1), (uint32_t)j, chain_id,
+                                                     (draw_type == 0 ? 1u : 2u) + 4u * lane, prm.rk));
             if (mailbox) {
                 // every warp gathers a share of the members: lane = component, all loads of a
                 // round in flight together; a word is valid once it carries this iteration's tag
@@ -484,13 +518,26 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
             __syncthreads();
             PHASE_MARK(4);
 
-            // ---- posterior update (gibbs.py:210-211): warp 0 weights, warp 1 rates ----------
-            if (warp < 2) {
+            // ---- posterior update (gibbs.py:210-211) ----------------------------------------
+            // Every warp runs ONE Marsaglia-Tsang trial per component, straight-line: even
+            // warps for the Dirichlet gammas, odd warps for the rate gammas, warp >> 1 = trial
+            // index.  Warp 0 then takes, per component, the first accepted trial -- the same
+            // variate a sequential rejection loop would return, without its latency.
+            {
                 unsigned cnt = 0;
                 unsigned long long sum = 0;
 #pragma unroll
                 for (int w = 0; w < WARPS; ++w) { cnt += s_tot_c[w][lane]; sum += s_tot_s[w][lane]; }
                 const bool live = lane < kreal;
+                const float fcnt = (float)cnt;
+                const float shape = (draw_type == 0 ? wh : rh_a) + fcnt;
+                if (!inject_coef) {
+                    const GammaTrial t = trial_finish(shape < 1.0f ? shape + 1.0f : shape, rnd);
+                    s_try_g[draw_type][warp >> 1][lane] = t.ok ? t.g : __int_as_float(0x7fc00000);
+                    s_try_b[draw_type][warp >> 1][lane] = rnd.l2_boost;
+                }
+                PHASE_MARK(5);                             // gamma trials
+                __syncthreads();
                 if (warp == 0) {
                     if (trace && task.team_rank == 0 && live) {
                         const size_t o = ((size_t)r * niter + (j - 1)) * kreal + lane;
@@ -501,29 +548,39 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
                     const unsigned keyv = live ? ((cnt << 5) | (unsigned)(31 - lane)) : 0u;
                     const unsigned best = __reduce_max_sync(FULL, keyv);
                     if (lane == 0) s_dom = 31 - (int)(best & 31u);
-                }
-                if (!inject_coef) {
-                    const float fcnt = (float)cnt;
-                    if (warp == 1) {
-                        float rate = 0.0f;
-                        if (live) {
-                            const float g = gamma_draw(rh_a + fcnt, (uint32_t)j, chain_id, 2u + 4u * lane, key0, key1);
-                            rate = g / fmaf((float)sum, ts, rh_b);
+                    if (!inject_coef) {
+                        float g[2], l2b[2];
+                        const float shapes[2] = {wh + fcnt, rh_a + fcnt};
+#pragma unroll
+                        for (int ty = 0; ty < 2; ++ty) {
+                            g[ty] = __int_as_float(0x7fc00000);
+                            l2b[ty] = 0.0f;
+#pragma unroll
+                            for (int tr = NTRIALS - 1; tr >= 0; --tr) {
+                                const float cand = s_try_g[ty][tr][lane];
+                                if (cand == cand) { g[ty] = cand; l2b[ty] = s_try_b[ty][tr][lane]; }
+                            }
+                            if (live && !(g[ty] == g[ty]))     // all parallel trials rejected (rare): go on serially
+                                g[ty] = gamma_serial(shapes[ty] < 1.0f ? shapes[ty] + 1.0f : shapes[ty], NTRIALS,
+                                                     (uint32_t)j, chain_id, (ty == 0 ? 1u : 2u) + 4u * lane, key0, key1, l2b[ty]);
                         }
-                        s_rate[lane] = rate;
-                        s_l2r[lane] = __log2f(rate);
-                    }
-                    float l2y = -INFINITY;
-                    if (warp == 0 && live)
-                        l2y = gamma_log2_draw(wh + fcnt, (uint32_t)j, chain_id, 1u + 4u * lane, key0, key1);
-                    PHASE_MARK(5);                             // gamma draws
-                    named_barrier_sync(1, 64);
-                    if (warp == 0) {
+                        // shape < 1 boost G(a) = G(a+1) U^(1/a): in log2 space for the weights (U^K underflows)
+                        float l2y = -INFINITY, rate = 0.0f;
+                        if (live) {
+                            l2y = __log2f(g[0]);
+                            if (shapes[0] < 1.0f) l2y += __fdividef(l2b[0], shapes[0]);
+                            float gr = g[1];
+                            if (shapes[1] < 1.0f) gr *= fast_exp2(__fdividef(l2b[1], shapes[1]));
+                            rate = __fdividef(gr, fmaf((float)sum, ts, rh_b));
+                        }
                         const float mx = warp_max(l2y);
                         const float tot = warp_sum(live ? fast_exp2(l2y - mx) : 0.0f);
                         const float l2w = l2y - mx - __log2f(tot);
-                        const float rate = s_rate[lane];
-                        if (live) s_coef[lane] = make_float2(l2w + s_l2r[lane], rate * (ts * LOG2E));
+                        const float2 ca = make_float2(l2w + __log2f(rate), rate * (ts * LOG2E));
+                        if (live) s_coef[lane] = ca;
+                        // a usable row: every slope finite and >= 0, every intercept finite or -inf (a dead
+                        // component), at least one alive -- then each datum's max term is exactly 1
+                        bad |= (live && !coef_ok(ca)) || !__any_sync(FULL, live && ca.x > -INFINITY);
                         if (save && task.team_rank == 0 && live && row < rows) {
                             const size_t o = ((size_t)r * rows + row) * kreal + lane;
                             b.mcweights[o] = exp2((double)l2w);
@@ -591,9 +648,13 @@ struct Variant { int k; kernel_fn fast; kernel_fn exact; };
 
 #define BRTA_VARIANT(KK) {KK, gibbs_sweep_kernel<KK, false>, gibbs_sweep_kernel<KK, true>}
 const Variant g_variants[] = {
+#ifdef BRTA_ONLY_K15                                       // developer builds: one instantiation, fast compile
+    BRTA_VARIANT(15),
+#else
     BRTA_VARIANT(2),  BRTA_VARIANT(3),  BRTA_VARIANT(4),  BRTA_VARIANT(5),  BRTA_VARIANT(6),
     BRTA_VARIANT(8),  BRTA_VARIANT(10), BRTA_VARIANT(12), BRTA_VARIANT(15), BRTA_VARIANT(16),
     BRTA_VARIANT(20), BRTA_VARIANT(24), BRTA_VARIANT(30), BRTA_VARIANT(32),
+#endif
 };
 
 const Variant* pick_variant(int ncomp)

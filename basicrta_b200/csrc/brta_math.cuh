@@ -66,59 +66,67 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 // 2 -> accept uniform, 3 -> boost uniform.  The squeeze test accepts ~92 % of the trials
 // without a logarithm; the exact test needs log(v) accurately (v is within 1e-3 of 1 for
 // the large shapes 1 + n_k), hence log1pf there and MUFU-grade intrinsics elsewhere.
-// Returns d*v with d = a - 1/3 for the (possibly boosted) shape a >= 1.
-__device__ __forceinline__ float gamma_core(float a, uint32_t iter, uint32_t chain, uint32_t purpose,
-                                            uint32_t k0, uint32_t k1, uint32_t& boost_word)
+// A trial yields d*v with d = a - 1/3 for the (possibly boosted) shape a >= 1; the shape < 1
+// boost G(a) = G(a+1) U^(1/a) is applied by the caller (in log2 space for the weights: an
+// empty component has Dirichlet shape 1/K (gibbs.py:173), where U^K underflows float32).
+// The part of a trial that does not depend on the shape: computed while the team exchange is
+// still in flight, so only ~40 instructions remain on the critical path once n_k is known.
+struct TrialRandoms {
+    float z;          // standard normal (Box-Muller, words 0 and 1)
+    float u;          // accept uniform in (0,1) (word 2)
+    float log_u;      // ln u
+    float squeeze;    // 1 - 0.0331 z^4
+    float l2_boost;   // log2 of the boost uniform in (0,1] (word 3)
+};
+
+__device__ __forceinline__ TrialRandoms trial_randoms(const Words4& w)
+{
+    TrialRandoms r;
+    const float u1 = word_to_unit_open_low(w.x);
+    const float u2 = word_to_unit(w.y);
+    float rad;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-2.0f * __logf(u1)));
+    r.z = rad * __cosf(6.283185307179586f * u2);
+    r.u = word_to_unit_open(w.z);
+    r.log_u = __logf(r.u);
+    const float z2 = r.z * r.z;
+    r.squeeze = 1.0f - 0.0331f * z2 * z2;
+    r.l2_boost = __log2f(word_to_unit_open_low(w.w));
+    return r;
+}
+
+struct GammaTrial { float g; bool ok; };
+
+// Finish a trial for shape a >= 1: straight-line, both acceptance tests evaluated.  The exact
+// test needs log(v) accurately (v is within 1e-3 of 1 for the large shapes 1 + n_k): log1pf.
+__device__ __forceinline__ GammaTrial trial_finish(float a, const TrialRandoms& r)
 {
     const float d = a - (1.0f / 3.0f);
     const float c = rsqrtf(9.0f * d);
-    float result = d;                                     // fallback: never reached in practice
-    boost_word = 0x80000000u;
-    for (uint32_t trial = 0; trial < 64u; ++trial) {
-        const Words4 w = philox4x32_10(trial, iter, chain, purpose, k0, k1);
-        const float u1 = word_to_unit_open_low(w.x);
-        const float u2 = word_to_unit(w.y);
-        const float z = sqrtf(-2.0f * __logf(u1)) * __cosf(6.283185307179586f * u2);
-        const float x = c * z;
-        if (x <= -1.0f) continue;
-        const float t = 1.0f + x;
-        const float v = t * t * t;
-        const float u = word_to_unit_open(w.z);
-        const float z2 = z * z;
-        bool ok = u < 1.0f - 0.0331f * z2 * z2;
-        if (!ok) ok = __logf(u) < 0.5f * z2 + d * (1.0f - v + 3.0f * log1pf(x));
-        if (ok) {
-            result = d * v;
-            boost_word = w.w;
+    const float x = c * r.z;
+    const float t = 1.0f + x;
+    const float v = t * t * t;
+    const bool exact = r.log_u < 0.5f * r.z * r.z + d * (1.0f - v + 3.0f * log1pf(fmaxf(x, -0.999999f)));
+    return GammaTrial{d * v, (x > -1.0f) && (r.u < r.squeeze || exact)};
+}
+
+// Sequential rejection loop from trial `first` on: the fallback after the parallel trials
+// (and the definition of the draw: the first accepted trial in counter order).
+__device__ __noinline__ float gamma_serial(float a, uint32_t first, uint32_t iter, uint32_t chain, uint32_t purpose,
+                                           uint32_t k0, uint32_t k1, float& l2_boost)
+{
+    float result = a - (1.0f / 3.0f);                     // never reached in practice
+    l2_boost = -1.0f;
+    for (uint32_t trial = first; trial < first + 64u; ++trial) {
+        const TrialRandoms r = trial_randoms(philox4x32_10(trial, iter, chain, purpose, k0, k1));
+        const GammaTrial t = trial_finish(a, r);
+        if (t.ok) {
+            result = t.g;
+            l2_boost = r.l2_boost;
             break;
         }
     }
     return result;
-}
-
-// Gamma(shape, 1) in linear space (rates: shape = 1 + n_k >= 1 with the default prior).
-__device__ __forceinline__ float gamma_draw(float shape, uint32_t iter, uint32_t chain, uint32_t purpose,
-                                            uint32_t k0, uint32_t k1)
-{
-    const bool boost = shape < 1.0f;
-    uint32_t bw;
-    float g = gamma_core(boost ? shape + 1.0f : shape, iter, chain, purpose, k0, k1, bw);
-    if (boost) g *= fast_exp2(__log2f(word_to_unit_open_low(bw)) / shape);
-    return g;
-}
-
-// log2 of a Gamma(shape, 1) variate.  The shape < 1 boost G(a) = G(a+1) U^(1/a) stays in
-// log space: an empty component has Dirichlet shape 1/K (gibbs.py:173), where U^K
-// underflows float32; the sampler only ever needs log w_k.
-__device__ __forceinline__ float gamma_log2_draw(float shape, uint32_t iter, uint32_t chain,
-                                                 uint32_t purpose, uint32_t k0, uint32_t k1)
-{
-    const bool boost = shape < 1.0f;
-    uint32_t bw;
-    const float g = gamma_core(boost ? shape + 1.0f : shape, iter, chain, purpose, k0, k1, bw);
-    float l2 = __log2f(g);
-    if (boost) l2 += __log2f(word_to_unit_open_low(bw)) / shape;
-    return l2;
 }
 
 }  // namespace brta

@@ -16,7 +16,10 @@ n_chains, n, niter = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 K = int(sys.argv[4]) if len(sys.argv) > 4 else 15
 rng = np.random.default_rng(1)
 chains = []
-for r in range(n_chains):
+if n == 0:                                                # the bench workload (C2): first n_chains residues
+    import bench
+    chains = [ChainInput(ticks=t, ts=0.1, chain_id=i) for i, t in enumerate(bench.workload(range(n_chains)))]
+for r in range(n_chains if n else 0):
     comp = rng.choice(3, size=n, p=[0.9, 0.09, 0.01])
     x = rng.exponential(1.0 / np.array([5, 0.05, 0.001])[comp])
     chains.append(ChainInput(ticks=np.maximum(np.ceil(x / 0.1), 1).astype(np.int64), ts=0.1, chain_id=r))
