@@ -31,6 +31,7 @@ FLAG_TRACE = 8
 
 STATUS_OK = 0
 STATUS_NONFINITE = 1
+STATUS_TIMEOUT = 2
 
 
 class BrtaError(RuntimeError):

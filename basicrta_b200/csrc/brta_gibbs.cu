@@ -38,6 +38,7 @@ namespace brta {
 
 constexpr int THREADS = BRTA_THREADS;
 constexpr int WARPS = THREADS / 32;
+constexpr unsigned SPIN_LIMIT = 1u << 25;                 // ~30 s of 1 us polls
 constexpr int NTRIALS = WARPS / 2;                        // Marsaglia-Tsang trials run in parallel per draw
 
 // exchange workspace of one chain (BRTA_EXCH_STRIDE bytes):
@@ -313,6 +314,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
     __shared__ float s_try_g[2][NTRIALS][32];              // parallel Marsaglia-Tsang trials: d*v or NaN
     __shared__ float s_try_b[2][NTRIALS][32];              //   and log2 of the shape < 1 boost uniform
     __shared__ unsigned s_bad;
+    __shared__ unsigned s_abort;                           // rendezvous watchdog tripped
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -380,7 +382,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
         }
         s_tot_c[warp][lane] = 0;
         s_tot_s[warp][lane] = 0;
-        if (tid == 0) { s_dom = 0; s_bad = 0; }
+        if (tid == 0) { s_dom = 0; s_bad = 0; s_abort = 0; }
         __syncthreads();
 
         // slice totals (warp 0) and per-component priors, lane = component
@@ -465,7 +467,11 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
                         atomicAdd(ex_arrive, 1u);
                     }
                     const unsigned target = (unsigned)team * (unsigned)j;
-                    while (ld_acquire_u32(ex_arrive) < target) __nanosleep(40);
+                    unsigned spins = 0;
+                    while (ld_acquire_u32(ex_arrive) < target) {
+                        if (++spins > SPIN_LIMIT) { s_abort = 1u; break; }
+                        __nanosleep(spins < 64u ? 40 : 1000);
+                    }
                     s_tot_c[0][lane] = ld_relaxed_u32(&ex_cnt[buf * 32 + lane]);
                     s_tot_s[0][lane] = ld_relaxed_u64(&ex_sum[buf * 32 + lane]);
                     if (task.team_rank == 0) {             // recycle the buffer last read in j-1
@@ -494,6 +500,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
 #pragma unroll
                     for (int i = 0; i < MAXM; ++i)
                         if (warp + i * WARPS < team) pend |= 1u << i;
+                    unsigned spins = 0;
                     while (pend) {
                         ulonglong2 v[MAXM];
 #pragma unroll
@@ -508,7 +515,13 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
                                 pend &= ~(1u << i);
                             }
                         }
-                        if (pend) __nanosleep(20);
+                        if (pend) {
+                            // watchdog: a teammate that never posts (a scheduling bug, a lost GPU) must
+                            // not hang the device; legitimate waits (a teammate still finishing its
+                            // previous wave) are seconds at most
+                            if (++spins > SPIN_LIMIT) { s_abort = 1u; break; }
+                            __nanosleep(spins < 64u ? 20 : 1000);
+                        }
                     }
                 }
                 s_tot_c[warp][lane] = acc_c;
@@ -517,6 +530,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
             PHASE_MARK(3);                                 // gather (waits for the team's slowest member)
             __syncthreads();
             PHASE_MARK(4);
+            if (s_abort) break;                            // uniform: written before the barrier
 
             // ---- posterior update (gibbs.py:210-211) ----------------------------------------
             // Every warp runs ONE Marsaglia-Tsang trial per component, straight-line: even
@@ -597,6 +611,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
         if (bad) atomicOr(&s_bad, 1u);
         __syncthreads();
         if (tid == 0 && s_bad) atomicOr(reinterpret_cast<unsigned*>(&b.status[r]), (unsigned)BRTA_STATUS_NONFINITE);
+        if (tid == 0 && s_abort) atomicOr(reinterpret_cast<unsigned*>(&b.status[r]), (unsigned)BRTA_STATUS_TIMEOUT);
         __syncthreads();
     }
 }

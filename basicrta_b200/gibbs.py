@@ -168,6 +168,8 @@ class Gibbs(object):
 
 
 def _raise_on_status(residue, status):
+    if status & _cabi.STATUS_TIMEOUT:
+        raise _cabi.BrtaError(f'residue {residue}: team rendezvous timed out on the device (status {status})')
     if status != _cabi.STATUS_OK:
         raise FloatingPointError(f'residue {residue}: sampler saw a non-finite likelihood (status {status})')
 

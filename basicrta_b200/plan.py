@@ -67,6 +67,41 @@ def _allocate_wave(quads, cmin, grid):
     return team, dmax
 
 
+def _assign_ctas(n_quads, order, groups, alloc, grid, overhead_quads):
+    """Gang list-scheduling of the teams on the CTAs.  CTAs never synchronise between waves,
+    so a CTA that finishes its wave-w task early can start its wave-(w+1) task early: within a
+    wave the teams with the longest slices take the CTAs that become free first, which absorbs
+    most of the integer-rounding slack of the previous wave.  Time unit: one quad of one
+    iteration (+ a fixed per-iteration overhead); a team starts when its last member is free.
+    Returns (team sizes, wave of chain, per-CTA task lists, simulated makespan)."""
+    R = len(n_quads)
+    team_size = np.zeros(R, dtype=np.int32)
+    wave_of = np.zeros(R, dtype=np.int32)
+    per_cta = [[] for _ in range(grid)]
+    free_at = np.zeros(grid, dtype=np.float64)
+    for w, ((a, b), team) in enumerate(zip(groups, alloc)):
+        members = [(int(order[a + i]), int(c)) for i, c in enumerate(team)]
+        slice_len = {r: -(-int(n_quads[r]) // c) for r, c in members}
+        members.sort(key=lambda rc: -slice_len[rc[0]])
+        avail = list(np.argsort(free_at, kind='stable'))         # earliest-free CTAs first
+        pos = 0
+        for r, c in members:
+            ctas = avail[pos:pos + c]
+            pos += c
+            q = int(n_quads[r])
+            team_size[r], wave_of[r] = c, w
+            base, rem = divmod(q, c)
+            start = max(free_at[x] for x in ctas)
+            begin = 0
+            for rank, x in enumerate(ctas):
+                cnt = base + (1 if rank < rem else 0)
+                per_cta[int(x)].append((r, c, rank, begin, cnt, w))
+                begin += cnt
+                free_at[x] = start + slice_len[r] + overhead_quads
+        assert pos <= grid
+    return team_size, wave_of, per_cta, float(free_at.max())
+
+
 def _group_contiguous(quads_sorted, cmin_sorted, n_waves, grid):
     """Split the (descending) chain list into n_waves contiguous groups of similar total
     work, each feasible for one wave (count <= grid, sum of minimum teams <= grid)."""
@@ -110,37 +145,13 @@ def build_plan(n_quads, grid, cap_quads, overhead_quads=DEFAULT_OVERHEAD_QUADS, 
     best = None
     for W in candidates:
         groups = _group_contiguous(qs, cs, W, grid)
-        cost, alloc = 0.0, []
-        for (a, b) in groups:
-            team, dmax = _allocate_wave(qs[a:b], cs[a:b], grid)
-            alloc.append(team)
-            cost += dmax + overhead_quads
+        alloc = [_allocate_wave(qs[a:b], cs[a:b], grid)[0] for (a, b) in groups]
+        cost = _assign_ctas(n_quads, order, groups, alloc, grid, overhead_quads)[3]
         if best is None or cost < best[0] - 1e-9:
             best = (cost, groups, alloc)
     cost, groups, alloc = best
 
-    team_size = np.zeros(R, dtype=np.int32)
-    wave_of = np.zeros(R, dtype=np.int32)
-    per_cta = [[] for _ in range(grid)]
-    sum_dmax = 0
-    for w, ((a, b), team) in enumerate(zip(groups, alloc)):
-        cta = 0
-        dmax = 0
-        for local, c in enumerate(team):
-            r = int(order[a + local])
-            q = int(n_quads[r])
-            c = int(c)
-            team_size[r], wave_of[r] = c, w
-            base, rem = divmod(q, c)
-            begin = 0
-            for rank in range(c):
-                cnt = base + (1 if rank < rem else 0)
-                per_cta[cta].append((r, c, rank, begin, cnt, w))
-                begin += cnt
-                dmax = max(dmax, cnt)
-                cta += 1
-        assert cta <= grid
-        sum_dmax += dmax
+    team_size, wave_of, per_cta, makespan = _assign_ctas(n_quads, order, groups, alloc, grid, overhead_quads)
 
     flat, begin = [], np.zeros(grid + 1, dtype=np.int32)
     for bidx, lst in enumerate(per_cta):
@@ -150,7 +161,7 @@ def build_plan(n_quads, grid, cap_quads, overhead_quads=DEFAULT_OVERHEAD_QUADS, 
     return Plan(tasks=tasks, cta_task_begin=begin, grid=grid,
                 slice_cap_quads=int(tasks['quad_count'].max()), n_waves=len(groups),
                 team_size=team_size, wave_of_chain=wave_of,
-                est_efficiency=float(n_quads.sum()) / (grid * max(sum_dmax, 1)))
+                est_efficiency=float(n_quads.sum()) / (grid * max(makespan, 1.0)))
 
 
 def shard_chains(costs, n_shards):

@@ -55,7 +55,8 @@ extern "C" {
 
 /* per-chain status words written by the kernel */
 #define BRTA_STATUS_OK        0
-#define BRTA_STATUS_NONFINITE 1   /* a datum saw a non-finite / zero total probability */
+#define BRTA_STATUS_NONFINITE 1   /* a coefficient row was not finite / had no live component */
+#define BRTA_STATUS_TIMEOUT   2   /* a team rendezvous timed out (watchdog); results invalid   */
 
 typedef struct brta_caps {
     int32_t abi_version;

@@ -3,6 +3,7 @@
     BRTA_LIB=basicrta_b200/libbrta_gibbs_dbg.so python tools/phase_timing.py 40 30000 1000
 """
 import ctypes as C
+import os
 import sys
 
 import numpy as np
@@ -23,8 +24,12 @@ for r in range(n_chains if n else 0):
     comp = rng.choice(3, size=n, p=[0.9, 0.09, 0.01])
     x = rng.exponential(1.0 / np.array([5, 0.05, 0.001])[comp])
     chains.append(ChainInput(ticks=np.maximum(np.ceil(x / 0.1), 1).astype(np.int64), ts=0.1, chain_id=r))
-eng = get_engine(0)
-db = eng.prepare(chains, K, niter, thin=100, seed=1)
+from basicrta_b200.engine import GibbsEngine
+cps = os.environ.get('BRTA_CTAS_PER_SM')
+eng = GibbsEngine(0, ctas_per_sm=int(cps) if cps else None)
+nw = os.environ.get('BRTA_WAVES')
+db = eng.prepare(chains, K, niter, thin=100, seed=1, n_waves=int(nw) if nw else None)
+print('waves', db.plan.n_waves, 'est eff', round(db.plan.est_efficiency, 3))
 buf = torch.zeros(db.plan.grid * 8, dtype=torch.int64, device='cuda')
 lib = _cabi.load()
 assert lib.brta_debug_set_phase_buffer(C.c_void_p(buf.data_ptr())) == 0
