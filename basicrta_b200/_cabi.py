@@ -18,6 +18,12 @@ THREADS = 128
 MAX_NCOMP = 32
 TICK_LIMIT = 1 << 23
 MAILBOX_MAX_TEAM = 32
+MAX_SHARDS = 16
+SHARD_TOTALS_BYTES = 3 * 32 * 16 + 128
+
+
+def shard_mailbox_bytes(g):
+    return 2 * g * 32 * 32
 
 
 def exch_bytes(team):
@@ -67,12 +73,15 @@ class Batch(C.Structure):
         ('inj_c', C.c_void_p), ('inj_a', C.c_void_p), ('inj_u', C.c_void_p),
         ('inj_u_offset', C.c_void_p), ('trace_nk', C.c_void_p), ('trace_tk', C.c_void_p),
         ('tasks', C.c_void_p), ('cta_task_begin', C.c_void_p), ('grid_ctas', C.c_int32),
-        ('slice_cap_quads', C.c_int32), ('exchange', C.c_void_p), ('exch_offset', C.c_void_p),
+        ('slice_cap_quads', C.c_int32),
+        ('n_shards', C.c_int32), ('shard_rank', C.c_int32), ('shard_mailbox', C.c_void_p),
+        ('shard_totals', C.c_void_p),
+        ('exchange', C.c_void_p), ('exch_offset', C.c_void_p),
     ]
 
 
 EXPORTS = ('brta_abi_version', 'brta_last_error', 'brta_query', 'brta_gibbs_launch_info',
-           'brta_gibbs_run_batch', 'brta_philox_fill', 'brta_mufu_probe')
+           'brta_gibbs_run_batch', 'brta_philox_fill', 'brta_mufu_probe', 'brta_enable_peer_access')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
@@ -113,6 +122,7 @@ def load():
     lib.brta_gibbs_run_batch.argtypes = [C.POINTER(Batch), C.c_void_p]
     lib.brta_philox_fill.argtypes = [C.c_void_p, C.c_int64, C.c_uint32, C.c_uint32, C.c_uint32,
                                      C.c_uint32, C.c_uint64, C.c_void_p]
+    lib.brta_enable_peer_access.argtypes = [C.c_int, C.c_int]
     lib.brta_mufu_probe.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     for name in EXPORTS:
         getattr(lib, name)

@@ -71,6 +71,21 @@ __device__ __forceinline__ void st_relaxed_v2(ulonglong2* p, unsigned long long 
 {
     asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" :: "l"(p), "l"(a), "l"(b) : "memory");
 }
+// system scope: words exchanged between GPUs over NVLink (peer-mapped memory)
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
 {
     unsigned long long v;
@@ -337,7 +352,9 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
         const int nq = task.quad_count;
         const int qb = task.quad_begin;
         const int team = task.team_size;
-        const bool mailbox = team > 1 && team <= BRTA_MAILBOX_MAX_TEAM;
+        const int n_shards = b.n_shards > 1 ? b.n_shards : 1;
+        const bool sharded = n_shards > 1;                 // the chain continues on other GPUs
+        const bool mailbox = !sharded && team > 1 && team <= BRTA_MAILBOX_MAX_TEAM;
         const uint32_t chain_id = b.chain_id[r];
         const float ts = b.ts[r];
         const int64_t tick_off = b.tick_offset[r];
@@ -445,7 +462,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
                 const unsigned oc = __reduce_add_sync(FULL, cnt);
                 const unsigned os = __reduce_add_sync(FULL, sum);
                 if (lane == dom) { cnt = slice_n - oc; sum = (unsigned)(slice_t - os); }
-                if (team == 1) {
+                if (team == 1 && !sharded) {
                     s_tot_c[0][lane] = cnt;
                     s_tot_s[0][lane] = sum;
                 } else if (mailbox) {
@@ -472,13 +489,71 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
                         if (++spins > SPIN_LIMIT) { s_abort = 1u; break; }
                         __nanosleep(spins < 64u ? 40 : 1000);
                     }
-                    s_tot_c[0][lane] = ld_relaxed_u32(&ex_cnt[buf * 32 + lane]);
-                    s_tot_s[0][lane] = ld_relaxed_u64(&ex_sum[buf * 32 + lane]);
+                    unsigned tot_c = ld_relaxed_u32(&ex_cnt[buf * 32 + lane]);
+                    unsigned long long tot_s = ld_relaxed_u64(&ex_sum[buf * 32 + lane]);
                     if (task.team_rank == 0) {             // recycle the buffer last read in j-1
                         const int old = (j + 2) % 3;
                         ex_cnt[old * 32 + lane] = 0u;
                         ex_sum[old * 32 + lane] = 0ull;
                     }
+                    if (sharded) {
+                        // second level: this GPU's totals go to every GPU's mailbox over NVLink as tagged
+                        // 64-bit words {iteration | n_k}, {iteration | sum lo}, {iteration | sum hi}; the
+                        // local leader adds up all shards and publishes the result to the local team
+                        unsigned long long* const glob = reinterpret_cast<unsigned long long*>(b.shard_totals);
+                        unsigned* const glob_flag = reinterpret_cast<unsigned*>(
+                            static_cast<unsigned char*>(b.shard_totals) + 3 * 32 * 16);
+                        unsigned long long* const gslot = glob + ((size_t)(j % 3) * 32 + lane) * 2;
+                        if (task.team_rank == 0) {
+                            const unsigned long long tag = (unsigned long long)(unsigned)j << 32;
+                            const size_t slot = (((size_t)(j & 1) * n_shards + b.shard_rank) * 32 + lane) * 4;
+                            for (int g = 0; g < n_shards; ++g) {
+                                unsigned long long* const dst = static_cast<unsigned long long*>(b.shard_mailbox[g]) + slot;
+                                st_relaxed_sys_u64(dst + 0, tag | tot_c);
+                                st_relaxed_sys_u64(dst + 1, tag | (tot_s & 0xffffffffull));
+                                st_relaxed_sys_u64(dst + 2, tag | (tot_s >> 32));
+                            }
+                            const unsigned long long* const mine =
+                                static_cast<const unsigned long long*>(b.shard_mailbox[b.shard_rank]);
+                            unsigned all_c = 0;
+                            unsigned long long all_s = 0;
+                            for (int g = 0; g < n_shards; ++g) {
+                                const unsigned long long* const src = mine + (((size_t)(j & 1) * n_shards + g) * 32 + lane) * 4;
+                                unsigned long long w0, w1, w2;
+                                unsigned spins2 = 0;
+                                for (;;) {
+                                    w0 = ld_relaxed_sys_u64(src + 0);
+                                    w1 = ld_relaxed_sys_u64(src + 1);
+                                    w2 = ld_relaxed_sys_u64(src + 2);
+                                    if ((unsigned)(w0 >> 32) == (unsigned)j && (unsigned)(w1 >> 32) == (unsigned)j &&
+                                        (unsigned)(w2 >> 32) == (unsigned)j) break;
+                                    if (++spins2 > SPIN_LIMIT) { s_abort = 1u; break; }
+                                    __nanosleep(spins2 < 64u ? 100 : 1000);
+                                }
+                                all_c += (unsigned)w0;
+                                all_s += (w1 & 0xffffffffull) | (w2 << 32);
+                            }
+                            tot_c = all_c;
+                            tot_s = all_s;
+                            gslot[0] = tot_c;
+                            gslot[1] = tot_s;
+                            __syncwarp();
+                            if (lane == 0) {
+                                __threadfence();
+                                st_release_u32(glob_flag, (unsigned)j);
+                            }
+                        } else {
+                            unsigned spins2 = 0;
+                            while (ld_acquire_u32(glob_flag) < (unsigned)j) {
+                                if (++spins2 > SPIN_LIMIT) { s_abort = 1u; break; }
+                                __nanosleep(spins2 < 64u ? 100 : 1000);
+                            }
+                            tot_c = (unsigned)ld_relaxed_u64(gslot + 0);
+                            tot_s = ld_relaxed_u64(gslot + 1);
+                        }
+                    }
+                    s_tot_c[0][lane] = tot_c;
+                    s_tot_s[0][lane] = tot_s;
                 }
             }
             PHASE_MARK(2);                                 // partials + post
@@ -750,6 +825,12 @@ int brta_gibbs_run_batch(const brta_batch* batch, void* stream)
     }
     if ((b.flags & BRTA_FLAG_INJECT_U) && (!b.inj_u || !b.inj_u_offset))
         return brta::fail(BRTA_E_NULL, "INJECT_U needs inj_u and inj_u_offset");
+    if (b.n_shards > 1) {
+        if (b.n_chains != 1 || b.n_shards > BRTA_MAX_SHARDS || b.shard_rank < 0 || b.shard_rank >= b.n_shards)
+            return brta::fail(BRTA_E_RANGE, "sharded launch: n_chains must be 1 and 0 <= shard_rank < n_shards <= 16");
+        if (!b.shard_mailbox || !b.shard_totals)
+            return brta::fail(BRTA_E_NULL, "sharded launch needs shard_mailbox and shard_totals");
+    }
     if ((b.flags & BRTA_FLAG_TRACE) && (!b.trace_nk || !b.trace_tk))
         return brta::fail(BRTA_E_NULL, "TRACE needs trace_nk and trace_tk");
 
@@ -764,6 +845,20 @@ int brta_gibbs_run_batch(const brta_batch* batch, void* stream)
     e = cudaLaunchCooperativeKernel((const void*)fn, dim3((unsigned)b.grid_ctas), dim3(BRTA_THREADS), args,
                                     smem, (cudaStream_t)stream);
     if (e != cudaSuccess) return brta::cuda_fail(e, "cudaLaunchCooperativeKernel");
+    return 0;
+}
+
+int brta_enable_peer_access(int device, int peer)
+{
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return brta::cuda_fail(e, "cudaSetDevice");
+    int can = 0;
+    e = cudaDeviceCanAccessPeer(&can, device, peer);
+    if (e != cudaSuccess) return brta::cuda_fail(e, "cudaDeviceCanAccessPeer");
+    if (!can) return brta::fail(BRTA_E_DEVICE, "devices cannot access each other's memory (no NVLink / P2P)");
+    e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return 0; }
+    if (e != cudaSuccess) return brta::cuda_fail(e, "cudaDeviceEnablePeerAccess");
     return 0;
 }
 

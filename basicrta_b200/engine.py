@@ -145,9 +145,11 @@ class GibbsEngine:
         return plan
 
     # ---- pack + upload -------------------------------------------------------------------
-    def prepare(self, chains, ncomp, niter, thin=100, seed=0, flags=0, inject=None, n_waves=None):
+    def prepare(self, chains, ncomp, niter, thin=100, seed=0, flags=0, inject=None, n_waves=None, shard=None):
         """``chains``: list of :class:`ChainInput`.  ``inject``: dict with optional
-        ``coef_c``/``coef_a`` (list of [niter,K] float32) and ``u`` (list of [niter,N])."""
+        ``coef_c``/``coef_a`` (list of [niter,K] float32) and ``u`` (list of [niter,N]).
+        ``shard`` (internal, see :func:`run_sharded`): this GPU's part of ONE chain split over
+        several GPUs: dict(rank, n_shards, quad_begin, quad_count, mailbox_table)."""
         torch = self.torch
         dev = torch.device('cuda', self.device)
         R = len(chains)
@@ -168,12 +170,23 @@ class GibbsEngine:
             raise ValueError('ticks must lie in [0, 2^23)')
         tick_dtype = np.uint16 if max_tick < 65536 else np.uint32
 
-        plan = self._plan(n_data, K, flags, n_waves=n_waves)
+        if shard is not None:
+            if R != 1:
+                raise ValueError('a sharded launch holds exactly one chain')
+            sq0, snq = int(shard['quad_begin']), int(shard['quad_count'])
+            d0 = 4 * sq0                                              # first datum of this GPU's shard
+            n_local = np.array([min(int(n_data[0]), 4 * (sq0 + snq)) - d0], dtype=np.int64)
+            plan = self._plan(np.array([4 * snq]), K, flags, n_waves=n_waves)
+            plan.tasks['quad_begin'] += sq0                          # tasks carry GLOBAL quad indices
+        else:
+            d0 = 0
+            n_local = n_data
+            plan = self._plan(n_data, K, flags, n_waves=n_waves)
         if int(plan.team_size.max()) * int(niter) >= (1 << 31):
             raise ValueError('team_size * niter overflows the arrive counter')
 
-        pad8 = (n_data + 7) // 8 * 8
-        tick_offset = np.concatenate(([0], np.cumsum(pad8)[:-1])).astype(np.int64)
+        pad8 = (n_local + 7) // 8 * 8
+        tick_offset = np.concatenate(([0], np.cumsum(pad8)[:-1])).astype(np.int64) - d0
         ticks = np.zeros(int(pad8.sum()), dtype=tick_dtype)
         ts = np.zeros(R, dtype=np.float32)
         chain_id = np.zeros(R, dtype=np.uint32)
@@ -183,8 +196,8 @@ class GibbsEngine:
         init_a = np.zeros((R, K), dtype=np.float32)
         w0, r0 = initial_state(K)
         for r, ch in enumerate(chains):
-            t = np.asarray(ch.ticks)
-            ticks[tick_offset[r]:tick_offset[r] + len(t)] = t
+            t = np.asarray(ch.ticks)[d0:d0 + int(n_local[r])]
+            ticks[tick_offset[r] + d0:tick_offset[r] + d0 + len(t)] = t
             ts[r] = ch.ts
             chain_id[r] = np.uint32(ch.chain_id & 0xFFFFFFFF)
             whyper[r] = np.ones(K) / K if ch.whypers is None else ch.whypers
@@ -196,13 +209,13 @@ class GibbsEngine:
         for task in plan.tasks:
             r = task['chain']
             lo = tick_offset[r] + 4 * int(task['quad_begin'])
-            hi = min(lo + 4 * int(task['quad_count']), tick_offset[r] + n_data[r])
+            hi = min(lo + 4 * int(task['quad_count']), tick_offset[r] + d0 + n_local[r])
             if int(ticks[lo:hi].sum(dtype=np.int64)) >= (1 << 32):
                 raise ValueError('a slice holds more than 2^32 ticks; use a coarser ts')
 
-        ind_stride = n_data.astype(np.int32)
-        ind_bytes = rows * n_data
-        ind_offset = np.concatenate(([0], np.cumsum(ind_bytes)[:-1])).astype(np.int64)
+        ind_stride = n_local.astype(np.int32)
+        ind_bytes = rows * n_local
+        ind_offset = np.concatenate(([0], np.cumsum(ind_bytes)[:-1])).astype(np.int64) - d0
 
         T = {}
         h2d = 0
@@ -249,10 +262,17 @@ class GibbsEngine:
         b.mcrates = dev_zeros('mcrates', (R, max(rows, 1), K), torch.float64)
         b.indicator = dev_zeros('indicator', (max(int(ind_bytes.sum()), 1),), torch.uint8)
         b.status = dev_zeros('status', (R,), torch.int32)
-        exch_size = np.array([(_cabi.exch_bytes(int(c)) + 127) // 128 * 128 for c in plan.team_size], dtype=np.int64)
+        exch_size = np.array([(max(_cabi.exch_bytes(int(c)), 1280) + 127) // 128 * 128 for c in plan.team_size],
+                             dtype=np.int64)
         exch_offset = np.concatenate(([0], np.cumsum(exch_size)[:-1])).astype(np.int64)
         b.exchange = dev_zeros('exchange', (int(exch_size.sum()),), torch.uint8)
         b.exch_offset = up('exch_offset', exch_offset)
+
+        if shard is not None:
+            b.n_shards, b.shard_rank = int(shard['n_shards']), int(shard['rank'])
+            b.shard_mailbox = shard['mailbox_table'].data_ptr()
+            T['shard_mailbox_table'] = shard['mailbox_table']
+            b.shard_totals = dev_zeros('shard_totals', (_cabi.SHARD_TOTALS_BYTES,), torch.uint8)
 
         inject = inject or {}
         if flags & _cabi.FLAG_INJECT_COEF:
@@ -272,6 +292,8 @@ class GibbsEngine:
             b.trace_tk = dev_zeros('trace_tk', (R, niter, K), torch.int64)
 
         torch.cuda.current_stream(dev).synchronize()
+        if shard is not None:
+            n_data, ind_offset = n_local, ind_offset + d0            # host-side views are shard-local
         return DeviceBatch(batch=b, plan=plan, tensors=T, host=H, n_data=n_data, ind_offset=ind_offset,
                            rows=rows, ncomp=K, niter=int(niter), flags=int(flags), h2d_bytes=h2d,
                            units=float(n_data.sum()) * K * int(niter))
@@ -349,6 +371,60 @@ class GibbsEngine:
                           n_waves=n_waves)
         self.launch(db)
         return self.fetch(db)
+
+
+def run_sharded(chain, ncomp, niter, devices, thin=100, seed=0, flags=0, inject=None):
+    """ONE chain with its residence times sharded over several GPUs of a box (config C4 of
+    BASELINE.json): GPU g sweeps a contiguous range of the data; once per iteration the GPUs
+    exchange their integer (n_k, sum tick_k) through tagged words written into each other's
+    memory over NVLink, inside the persistent kernels -- there is no host round trip and no
+    NCCL call per iteration.  Every GPU then draws the identical posterior update from the same
+    Philox key.  Results are bit-identical to the single-GPU run (Philox is keyed by the global
+    datum index; the statistics are integers).
+
+    One host process drives all devices (peer access is enabled between every pair).
+    Returns one :class:`ChainResult` for the whole chain."""
+    import torch
+    devices = [int(d) for d in devices]
+    G = len(devices)
+    if not 1 <= G <= _cabi.MAX_SHARDS:
+        raise ValueError(f'1..{_cabi.MAX_SHARDS} devices')
+    engines = [get_engine(d) for d in devices]
+    lib = _cabi.load()
+    for a in devices:
+        for bdev in devices:
+            if a != bdev:
+                _cabi.check(lib.brta_enable_peer_access(a, bdev), 'brta_enable_peer_access')
+    n = len(chain.ticks)
+    nq = (n + 3) // 4
+    per = -(-nq // G)
+    per += per & 1                                               # even quad boundaries keep 16-byte alignment
+    bounds = [min(g * per, nq) for g in range(G + 1)]
+    if bounds[-2] >= nq:
+        raise ValueError('chain too short to shard over that many devices')
+    mailboxes = [torch.zeros(_cabi.shard_mailbox_bytes(G), dtype=torch.uint8, device=f'cuda:{d}') for d in devices]
+    ptrs = np.array([m.data_ptr() for m in mailboxes], dtype=np.int64)
+    batches = []
+    for g, (d, eng) in enumerate(zip(devices, engines)):
+        with torch.cuda.device(d):
+            table = torch.from_numpy(ptrs).to(f'cuda:{d}')
+            shard = dict(rank=g, n_shards=G, quad_begin=bounds[g], quad_count=bounds[g + 1] - bounds[g],
+                         mailbox_table=table)
+            batches.append(eng.prepare([chain], ncomp, niter, thin=thin, seed=seed, flags=flags, inject=inject,
+                                       shard=shard))
+    for d in devices:
+        torch.cuda.synchronize(d)
+    for eng, db in zip(engines, batches):                         # asynchronous launches: all kernels run concurrently
+        eng.launch(db)
+    parts = [eng.fetch(db)[0] for eng, db in zip(engines, batches)]
+    del mailboxes
+    first = parts[0]
+    status = 0
+    for p in parts:
+        status |= p.status
+    return ChainResult(mcweights=first.mcweights, mcrates=first.mcrates,
+                       indicator=np.concatenate([p.indicator for p in parts], axis=1), status=status,
+                       trace_nk=first.trace_nk, trace_tk=first.trace_tk)
 
 
 _engines = {}

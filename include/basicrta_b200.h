@@ -40,6 +40,11 @@ extern "C" {
  * of L2 atomics accumulators + an arrive counter */
 #define BRTA_EXCH_BYTES(team) ((team) <= BRTA_MAILBOX_MAX_TEAM ? 2 * (team) * 32 * 16 : 1280)
 
+/* cross-GPU exchange of a sharded chain: 2 parities x G sources x 32 components x 32 B */
+#define BRTA_SHARD_MAILBOX_BYTES(g) (2 * (g) * 32 * 32)
+#define BRTA_SHARD_TOTALS_BYTES     (3 * 32 * 16 + 128)
+#define BRTA_MAX_SHARDS 16
+
 /* brta_batch.flags */
 #define BRTA_FLAG_EXACT        1u   /* IEEE-only arithmetic (bit-exact vs oracle/gibbs_oracle.py) */
 #define BRTA_FLAG_INJECT_COEF  2u   /* teacher forcing: per-iteration (coef_c, coef_a) rows given  */
@@ -147,6 +152,17 @@ typedef struct brta_batch {
     const int32_t*   cta_task_begin; /* [grid_ctas + 1]                                  */
     int32_t          grid_ctas;    /* must equal sm_count * ctas_per_sm or less          */
     int32_t          slice_cap_quads; /* largest quad_count over all tasks               */
+    /* one chain sharded over several GPUs (config C4): n_shards > 1 requires n_chains == 1.  Each GPU
+     * sweeps a contiguous range of the chain's quads (tasks carry GLOBAL quad indices; tick_offset /
+     * ind_offset are shifted by the caller so that global indices address the local shard) and the GPUs
+     * exchange (n_k, sum tick_k) once per iteration through tagged words written into each other's
+     * memory over NVLink (peer access enabled by the caller, see brta_enable_peer_access). */
+    int32_t          n_shards;     /* G; 0 or 1 = not sharded                             */
+    int32_t          shard_rank;   /* this GPU's position 0..G-1                          */
+    void* const*     shard_mailbox;/* device array of G pointers: mailbox of every GPU, each
+                                      BRTA_SHARD_MAILBOX_BYTES(G) bytes, zeroed               */
+    void*            shard_totals; /* local, BRTA_SHARD_TOTALS_BYTES bytes, zeroed            */
+
     void*            exchange;     /* zeroed by the caller; chain r owns BRTA_EXCH_BYTES(team_size)
                                       bytes at exch_offset[r]                             */
     const int64_t*   exch_offset;  /* [R] byte offsets, multiples of 128                 */
@@ -169,6 +185,10 @@ int brta_gibbs_run_batch(const brta_batch* batch, void* stream);
  * `seed`: exposes the device generator to the known-answer tests. */
 int brta_philox_fill(uint32_t* out_dev, int64_t n, uint32_t x0, uint32_t c1, uint32_t c2,
                      uint32_t c3, uint64_t seed, void* stream);
+
+/* Let `device` read and write `peer`'s memory (cudaDeviceEnablePeerAccess; already enabled is
+ * not an error).  Needed once per ordered pair before a sharded launch. */
+int brta_enable_peer_access(int device, int peer);
 
 /* MUFU.EX2 throughput probe: `blocks` CTAs of 256 threads each execute 8*iters
  * ex2.approx (plus as many FADD).  Timed by the caller with CUDA events it yields the

@@ -153,3 +153,33 @@ def test_argument_validation(engine):
     from basicrta_b200.engine import times_to_ticks
     with pytest.raises(ValueError):
         times_to_ticks(np.array([0.1, 0.25, 0.3]), 0.1)      # not on the grid
+
+
+def _two_gpus():
+    import torch
+    return torch.cuda.device_count() >= 2
+
+
+@pytest.mark.skipif(not _two_gpus(), reason='needs 2 GPUs (gpurun --gpus 2)')
+def test_chain_sharded_over_two_gpus_is_bit_exact():
+    """Config C4 in miniature: one chain, its times split over 2 GPUs, per-iteration exchange of the
+    integer (n_k, sum tick_k) over peer memory inside the kernels.  Teacher-forced EXACT mode must match
+    the oracle bit for bit, and the free-running chain must equal the single-GPU chain."""
+    from basicrta_b200.engine import get_engine, run_sharded
+    K, niter, thin = 15, 12, 4
+    times = O.synth_times(60001, [0.9, 0.09, 0.01], [5, 0.05, 0.001], seed=4)
+    ticks = O.to_ticks(times, 0.1)
+    ref = O.run_teacher_forced(ticks, 0.1, K, niter, seed=6, chain_id=2, rng=np.random.default_rng(3), g=thin)
+    flags = _cabi.FLAG_EXACT | _cabi.FLAG_INJECT_COEF | _cabi.FLAG_TRACE
+    chain = ChainInput(ticks=ticks, ts=0.1, chain_id=2)
+    got = run_sharded(chain, K, niter, devices=[0, 1], thin=thin, seed=6, flags=flags,
+                      inject={'coef_c': [ref['coef_c']], 'coef_a': [ref['coef_a']]})
+    assert got.status == 0
+    assert np.array_equal(got.trace_nk, ref['nk']) and np.array_equal(got.trace_tk, ref['tk'])
+    assert np.array_equal(got.indicator, ref['indicator'])
+    # free running: 2 GPUs == 1 GPU, bit for bit
+    one = get_engine(0).run([chain], K, 300, thin=50, seed=9)[0]
+    two = run_sharded(chain, K, 300, devices=[0, 1], thin=50, seed=9)
+    assert two.status == 0
+    assert np.array_equal(one.mcrates, two.mcrates) and np.array_equal(one.mcweights, two.mcweights)
+    assert np.array_equal(one.indicator, two.indicator)
