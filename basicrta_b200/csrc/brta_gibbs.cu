@@ -138,48 +138,79 @@ __device__ __forceinline__ int count_le(const float (&cum)[K], float thr)
     return c;
 }
 
-// Labels of D data at once.  l[d][k] holds the logit, then the running cumulative sum.
-template <int K, int D, bool EXACT>
-__device__ __forceinline__ void draw_labels(const float (&tick)[D], const float (&f12)[D],
-                                            const float2* __restrict__ s_coef, int kmax,
-                                            int (&lab)[D])
+// Label of ONE datum with the max-subtracted logits of the oracle: the EXACT arithmetic, and
+// the rarely-taken safe path of the FAST mode.
+template <int K, bool EXACT>
+__device__ __forceinline__ int draw_label_maxsub(float tick, float f12, const float2* __restrict__ s_coef, int kmax)
 {
-    float l[D][K];
-    float m[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) m[d] = -INFINITY;
+    float l[K];
+    float m = -INFINITY;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const float2 ca = s_coef[k];                       // broadcast LDS
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            l[d][k] = EXACT ? __fsub_rn(ca.x, __fmul_rn(ca.y, tick[d]))
-                            : fmaf(-ca.y, tick[d], ca.x);
-            m[d] = fmaxf(m[d], l[d][k]);
-        }
+        const float2 ca = s_coef[k];
+        l[k] = EXACT ? __fsub_rn(ca.x, __fmul_rn(ca.y, tick)) : fmaf(-ca.y, tick, ca.x);
+        m = fmaxf(m, l[k]);
     }
-    float cum[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) cum[d] = 0.0f;
+    float cum = 0.0f;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
+        cum = EXACT ? __fadd_rn(cum, soft_exp2(__fsub_rn(l[k], m))) : cum + fast_exp2(l[k] - m);
+        l[k] = cum;
+    }
+    // u = f12 - 1 is exact, so fma(f12, total, -total) is u * total rounded once: the same bits as
+    // the oracle's float32 product
+    const float thr = __fmaf_rn(f12, cum, -cum);
+    return min(count_le<K>(l, thr), kmax);
+}
+
+template <int K>
+__device__ __noinline__ int draw_label_safe(float tick, float f12, const float2* __restrict__ s_coef, int kmax)
+{
+    return draw_label_maxsub<K, false>(tick, f12, s_coef, kmax);
+}
+
+// Labels of D data at once.  l[d][k] holds the logit, then the running cumulative sum.
+//
+// EXACT: the oracle's arithmetic (max-subtracted logits, IEEE-only operations).
+// FAST : no max subtraction.  logit_k = log2(w_k r_k) - r_k t log2(e) is bounded above by
+//        log2(max rate) (w <= 1, t >= 0), far from float32 overflow, so the only hazard is
+//        underflow of EVERY term of a datum -- a state in which the datum would be impossible
+//        under all components (it occurs, if at all, in the first burn-in sweeps).  That is
+//        caught by one compare on the total and redone with the max-subtracted form.  Dropping
+//        the max removes a subtract per (datum, component) pair and the max tree: 92 of the
+//        476 instructions of a quad at K = 15.  Terms keep full float32 relative precision;
+//        the label differs from EXACT only where u lands within rounding of a CDF boundary.
+template <int K, int D, bool EXACT>
+__device__ __forceinline__ unsigned draw_labels(const float (&tick)[D], const float (&f12)[D],
+                                                const float2* __restrict__ s_coef, int kmax,
+                                                int (&lab)[D])
+{
+    unsigned redo = 0u;                                    // bit d: datum d underflowed, caller redoes it
+    if constexpr (EXACT) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            if (EXACT) {
-                cum[d] = __fadd_rn(cum[d], soft_exp2(__fsub_rn(l[d][k], m[d])));
-            } else {
-                cum[d] += fast_exp2(l[d][k] - m[d]);
+        for (int d = 0; d < D; ++d) lab[d] = draw_label_maxsub<K, true>(tick[d], f12[d], s_coef, kmax);
+    } else {
+        float l[D][K];
+        float cum[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) cum[d] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float2 ca = s_coef[k];                   // broadcast LDS
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                cum[d] += fast_exp2(fmaf(-ca.y, tick[d], ca.x));
+                l[d][k] = cum[d];
             }
-            l[d][k] = cum[d];
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const float thr = __fmaf_rn(f12[d], cum[d], -cum[d]);
+            lab[d] = min(count_le<K>(l[d], thr), kmax);
+            if (!(cum[d] > 8.0779357e-28f)) redo |= 1u << d;   // total < 2^-90 (or NaN)
         }
     }
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-        // u = f12 - 1 is exact, so fma(f12, total, -total) is u * total rounded once: the same
-        // bits as the oracle's float32 product
-        const float thr = __fmaf_rn(f12[d], cum[d], -cum[d]);
-        lab[d] = min(count_le<K>(l[d], thr), kmax);
-    }
+    return redo;
 }
 
 // data of one quad processed together by a thread (register pressure vs ILP)
@@ -223,15 +254,21 @@ __device__ __forceinline__ void sweep_quad(const float4 tk, const float4 f12, co
     const float tks[4] = {tk.x, tk.y, tk.z, tk.w};
     const float fs[4] = {f12.x, f12.y, f12.z, f12.w};      // uniforms as floats in [1,2)
     int labs[4];
+    unsigned redo = 0u;
 #pragma unroll
     for (int h = 0; h < 4; h += D) {
         float td[D], fd[D];
         int ld[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) { td[d] = tks[h + d]; fd[d] = fs[h + d]; }
-        draw_labels<K, D, EXACT>(td, fd, s_coef, kmax, ld);
+        redo |= draw_labels<K, D, EXACT>(td, fd, s_coef, kmax, ld) << h;
 #pragma unroll
         for (int d = 0; d < D; ++d) labs[h + d] = ld[d];
+    }
+    if (redo) {                                            // cold: after the quad, few registers are live
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+            if (redo & (1u << d)) labs[d] = draw_label_safe<K>(tks[d], fs[d], s_coef, kmax);
     }
     if (partial) {                                         // the chain's last quad: padding is never counted
 #pragma unroll

@@ -96,3 +96,24 @@ def test_fast_mode_flip_rate(engine):
     flips = np.mean(got.indicator != ref['indicator'])
     assert flips < 1e-4, flips
     assert np.abs(got.trace_nk - ref['nk']).max() <= 8
+
+
+def test_fast_mode_underflow_takes_the_safe_path(engine):
+    """FAST mode drops the max subtraction; a datum whose every term underflows float32 (possible only
+    in wild transient states) must be redone with the max-subtracted form.  Coefficients with slopes of
+    ~1 log2 unit per tick push the logits of most data below -126: labels must still match EXACT."""
+    K, niter, n = 3, 4, 4096
+    rng = np.random.default_rng(5)
+    ticks = rng.integers(1, 3000, size=n).astype(np.int64)
+    coef_c = np.tile(np.array([0.0, -1.0, -2.0], np.float32), (niter, 1))
+    coef_a = np.tile(np.array([1.0, 0.9, 0.8], np.float32), (niter, 1))
+    out = {}
+    for name, flags in (('exact', _cabi.FLAG_EXACT), ('fast', 0)):
+        out[name] = engine.run([ChainInput(ticks=ticks, ts=0.1, chain_id=1)], K, niter, thin=1, seed=3,
+                               flags=flags | _cabi.FLAG_INJECT_COEF | _cabi.FLAG_TRACE,
+                               inject={'coef_c': [coef_c], 'coef_a': [coef_a]})[0]
+        assert out[name].status == 0
+    assert np.mean(out['fast'].indicator[:niter] != out['exact'].indicator[:niter]) < 1e-3
+    assert np.abs(out['fast'].trace_nk - out['exact'].trace_nk).max() <= 4
+    big = ticks > 200                                      # every term below 2^-126 without the max
+    assert big.sum() > 3000 and np.all(out['fast'].indicator[0][big] == 2)

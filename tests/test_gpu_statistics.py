@@ -93,17 +93,24 @@ def test_indicator_consistent_with_parameters(chains):
 
 
 def test_clustered_tau_matches_reference_posterior(chains):
-    """End of the pipeline: process_gibbs (host) on a GPU chain gives a slowest tau whose
-    interval covers the reference's posterior mean of 1/rate for the slow component."""
-    import tempfile
+    """End of the pipeline.  (1) The slowest significant tau = 1/rate per sample -- the quantity the
+    reference's tau estimate is built on -- has the reference's median within 2 %, chain by chain.
+    (2) process_gibbs (host GaussianMixture, restated from gibbs.py:221-308) runs on a GPU chain and
+    its 95 % interval for the slowest tau covers the reference median.  The clustered point estimate
+    itself is not compared: on this data set the reference's own chains split 44 % / 38 % between 3
+    and 4 components above the weight cut-off, so the cluster count (and with it the histogram-mode
+    estimate) flips from chain to chain for the reference as well."""
     from basicrta_b200.gibbs import Gibbs
-    (ref_w, ref_r), _, res = chains
+    (ref_w, ref_r), (got_w, got_r), res = chains
+    slow_ref = 1.0 / np.where(ref_w > 10.0 / N, ref_r, np.inf).min(axis=-1)
+    slow_got = 1.0 / np.where(got_w > 10.0 / N, got_r, np.inf).min(axis=-1)
+    for c in range(slow_got.shape[0]):
+        assert abs(np.median(slow_got[c]) / np.median(slow_ref) - 1) < 0.02, c
     times = O.synth_times(N, [0.90, 0.09, 0.01], [5, 0.05, 0.001], seed=20241109)
     gb = Gibbs(times, 'X1', 0, ncomp=K, niter=NITER, cutoff=7.0)
     gb._prepare()
     gb.mcweights, gb.mcrates, gb.indicator = res[0].mcweights, res[0].mcrates, res[0].indicator
     gb.process_gibbs(save=False)
     lo, tau, hi = gb.estimate_tau()
-    slow_ref = 1.0 / np.where(ref_w > 10.0 / N, ref_r, np.inf).min(axis=-1)
-    assert lo < np.median(slow_ref) < hi
-    assert abs(tau / np.median(slow_ref) - 1) < 0.25         # histogram-mode estimator: coarse by construction
+    assert lo < np.median(slow_ref) < hi and lo < tau < hi
+    assert gb.processed_results.ncomp in (3, 4)
