@@ -248,7 +248,7 @@ constexpr uint32_t TICK_BIAS = 0x4B000000u;
 template <int K, bool EXACT, bool SAVE>
 __device__ __forceinline__ void sweep_quad(const float4 tk, const float4 f12, const float2* __restrict__ s_coef,
                                            int kmax, int dom, int i0, int n_data, bool partial,
-                                           uint32_t stat_addr, uint8_t* ind_row)
+                                           uint32_t stat_addr, uint8_t* ind_row, const int32_t* __restrict__ perm)
 {
     constexpr int D = data_in_flight(K);
     const float tks[4] = {tk.x, tk.y, tk.z, tk.w};
@@ -282,7 +282,7 @@ __device__ __forceinline__ void sweep_quad(const float4 tk, const float4 f12, co
     if (SAVE) {                                            // 1 iteration in `thin`: dense [S,N] bytes
 #pragma unroll
         for (int d = 0; d < 4; ++d)
-            if (i0 + d < n_data) ind_row[i0 + d] = (uint8_t)labs[d];
+            if (i0 + d < n_data) ind_row[perm ? perm[i0 + d] : i0 + d] = (uint8_t)labs[d];
     }
 }
 
@@ -291,7 +291,7 @@ __device__ __forceinline__ void sweep_slice(const float4* __restrict__ s_tick4, 
                                             int nq, int qb, int n_data, int kmax, int dom, uint32_t j,
                                             uint32_t chain_id, const RoundKeys& rk,
                                             const float4* __restrict__ u_row, uint32_t stat_addr,
-                                            uint8_t* ind_row)
+                                            uint8_t* ind_row, const int32_t* __restrict__ perm)
 {
     // at most one quad of the whole chain is partial; find out once whether it is in this slice
     const int tail_q = ((n_data & 3) != 0) ? (n_data >> 2) - qb : -1;
@@ -306,7 +306,7 @@ __device__ __forceinline__ void sweep_slice(const float4* __restrict__ s_tick4, 
             f12 = make_float4(word_to_12(w.x), word_to_12(w.y), word_to_12(w.z), word_to_12(w.w));
         }
         sweep_quad<K, EXACT, SAVE>(tk, f12, s_coef, kmax, dom, (qb + q) * 4, n_data, q == tail_q,
-                                   stat_addr, ind_row);
+                                   stat_addr, ind_row, perm);
     }
 }
 
@@ -397,6 +397,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
         const int64_t tick_off = b.tick_offset[r];
         const int ind_stride = b.ind_stride[r];
         uint8_t* const ind_base = b.indicator + b.ind_offset[r];
+        const int32_t* const perm = b.perm ? b.perm + b.perm_offset[r] : nullptr;
         const float* const inj_u_base = inject_u ? b.inj_u + b.inj_u_offset[r] : nullptr;
         const size_t u_pitch = (size_t)((n_data + 3) / 4) * 4;
 
@@ -482,10 +483,10 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
             // ---- indicator draws + sufficient statistics (gibbs.py:196-207) -------------
             if (save)
                 sweep_slice<K, EXACT, true>(s_tick4, s_coef, nq, qb, n_data, kreal - 1, dom, (uint32_t)j, chain_id,
-                                            prm.rk, u_row, stat_addr, ind_base + (size_t)row * ind_stride);
+                                            prm.rk, u_row, stat_addr, ind_base + (size_t)row * ind_stride, perm);
             else
                 sweep_slice<K, EXACT, false>(s_tick4, s_coef, nq, qb, n_data, kreal - 1, dom, (uint32_t)j, chain_id,
-                                             prm.rk, u_row, stat_addr, nullptr);
+                                             prm.rk, u_row, stat_addr, nullptr, nullptr);
             PHASE_MARK(0);                                 // sweep
             __syncthreads();
             PHASE_MARK(1);                                 // wait for the CTA's slowest warp

@@ -100,6 +100,7 @@ class DeviceBatch:
     plan: object
     tensors: dict = field(default_factory=dict)      # keeps device memory alive
     host: dict = field(default_factory=dict)         # pinned host copies of the inputs
+    order: list = None                                # per chain: canonical position -> original index
     n_data: np.ndarray = None
     ind_offset: np.ndarray = None
     rows: int = 0
@@ -195,8 +196,10 @@ class GibbsEngine:
         init_c = np.zeros((R, K), dtype=np.float32)
         init_a = np.zeros((R, K), dtype=np.float32)
         w0, r0 = initial_state(K)
+        # canonical order: ascending ticks (stable).  Philox word p belongs to canonical position p.
+        order = [np.argsort(np.asarray(ch.ticks), kind='stable').astype(np.int32) for ch in chains]
         for r, ch in enumerate(chains):
-            t = np.asarray(ch.ticks)[d0:d0 + int(n_local[r])]
+            t = np.asarray(ch.ticks)[order[r]][d0:d0 + int(n_local[r])]
             ticks[tick_offset[r] + d0:tick_offset[r] + d0 + len(t)] = t
             ts[r] = ch.ts
             chain_id[r] = np.uint32(ch.chain_id & 0xFFFFFFFF)
@@ -240,6 +243,10 @@ class GibbsEngine:
         b.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         b.ticks = up('ticks', ticks.view(np.int16 if tick_dtype == np.uint16 else np.int32))
         b.tick_offset = up('tick_offset', tick_offset)
+        if shard is None:                                  # sharded runs keep canonical order, see run_sharded
+            perm_offset = np.concatenate(([0], np.cumsum(n_data)[:-1])).astype(np.int64)
+            b.perm = up('perm', np.concatenate(order))
+            b.perm_offset = up('perm_offset', perm_offset)
         b.n_data = up('n_data', n_data.astype(np.int32))
         b.chain_id = up('chain_id', chain_id.view(np.int32))
         b.ts = up('ts', ts)
@@ -282,9 +289,9 @@ class GibbsEngine:
             pitch = (n_data + 3) // 4 * 4
             u_off = np.concatenate(([0], np.cumsum(pitch * niter)[:-1])).astype(np.int64)
             u_all = np.zeros(int((pitch * niter).sum()), dtype=np.float32)
-            for r, u in enumerate(inject['u']):
+            for r, u in enumerate(inject['u']):                   # given per original datum -> canonical order
                 blk = u_all[u_off[r]:u_off[r] + pitch[r] * niter].reshape(niter, pitch[r])
-                blk[:, :n_data[r]] = np.asarray(u, np.float32)
+                blk[:, :n_data[r]] = np.asarray(u, np.float32)[:, order[r]]
             b.inj_u = up('inj_u', u_all)
             b.inj_u_offset = up('inj_u_offset', u_off)
         if flags & _cabi.FLAG_TRACE:
@@ -294,7 +301,7 @@ class GibbsEngine:
         torch.cuda.current_stream(dev).synchronize()
         if shard is not None:
             n_data, ind_offset = n_local, ind_offset + d0            # host-side views are shard-local
-        return DeviceBatch(batch=b, plan=plan, tensors=T, host=H, n_data=n_data, ind_offset=ind_offset,
+        return DeviceBatch(batch=b, plan=plan, tensors=T, host=H, order=order, n_data=n_data, ind_offset=ind_offset,
                            rows=rows, ncomp=K, niter=int(niter), flags=int(flags), h2d_bytes=h2d,
                            units=float(n_data.sum()) * K * int(niter))
 
@@ -422,8 +429,10 @@ def run_sharded(chain, ncomp, niter, devices, thin=100, seed=0, flags=0, inject=
     status = 0
     for p in parts:
         status |= p.status
-    return ChainResult(mcweights=first.mcweights, mcrates=first.mcrates,
-                       indicator=np.concatenate([p.indicator for p in parts], axis=1), status=status,
+    canonical = np.concatenate([p.indicator for p in parts], axis=1)     # shards hold canonical (sorted) order
+    indicator = np.empty_like(canonical)
+    indicator[:, batches[0].order[0]] = canonical
+    return ChainResult(mcweights=first.mcweights, mcrates=first.mcrates, indicator=indicator, status=status,
                        trace_nk=first.trace_nk, trace_tk=first.trace_tk)
 
 

@@ -120,6 +120,15 @@ typedef struct brta_batch {
                                       tick_offset a multiple of 8 elements, storage padded
                                       to a multiple of 4 elements per chain               */
     const int64_t*  tick_offset;   /* [R] element offsets                                */
+    const int32_t*  perm;          /* canonical order: the sampler walks a chain's data in ASCENDING
+                                      TICK order (stable) -- Philox word p belongs to the datum at
+                                      canonical position p, and equal ticks sit together so their
+                                      cumulative rows can be shared.  `ticks` holds each chain in
+                                      that order; perm[perm_offset[r] + p] is the original index of
+                                      position p and routes the stored labels back, so `indicator`
+                                      is in the caller's original datum order.  NULL: identity
+                                      (labels stay in canonical order)                          */
+    const int64_t*  perm_offset;   /* [R] element offsets into perm                        */
     const int32_t*  n_data;        /* [R] N_r                                            */
     const uint32_t* chain_id;      /* [R] Philox counter word identifying the chain      */
     const float*    ts;            /* [R] time step (gibbs.py:147-151)                   */

@@ -211,8 +211,29 @@ def posterior_numpy(nk, tk, ts, whypers, rhypers, rng):
     return weights, rates
 
 
+def canonical_order(ticks):
+    """The sampler walks a chain's data in ascending tick order (stable): position p of that
+    order consumes Philox word p.  Data are exchangeable in the model (basicrta/gibbs.py:196-207
+    never looks at their order), so this only fixes which uniform a datum gets."""
+    return np.argsort(np.asarray(ticks), kind='stable')
+
+
 def run_teacher_forced(ticks, ts, ncomp, niter, seed, chain_id, rng, g=100,
                        whypers=None, rhypers=None, uniforms=None):
+    """Whole chain in device arithmetic with a host-side posterior draw.  Data are processed in
+    :func:`canonical_order`; ``indicator`` (and ``uniforms``) are in the caller's original order."""
+    order = canonical_order(ticks)
+    out = _run_teacher_forced_canonical(np.asarray(ticks)[order], ts, ncomp, niter, seed, chain_id, rng, g=g,
+                                        whypers=whypers, rhypers=rhypers,
+                                        uniforms=None if uniforms is None else np.asarray(uniforms)[:, order])
+    ind = np.empty_like(out['indicator'])
+    ind[:, order] = out['indicator']
+    out['indicator'] = ind
+    return out
+
+
+def _run_teacher_forced_canonical(ticks, ts, ncomp, niter, seed, chain_id, rng, g=100,
+                                  whypers=None, rhypers=None, uniforms=None):
     """Whole chain in device arithmetic with a host-side posterior draw.
 
     Returns the outputs of :func:`allocate` plus the per-iteration traces the CUDA
