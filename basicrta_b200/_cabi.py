@@ -34,6 +34,7 @@ FLAG_EXACT = 1
 FLAG_INJECT_COEF = 2
 FLAG_INJECT_U = 4
 FLAG_TRACE = 8
+FLAG_NO_TABLE = 16
 
 STATUS_OK = 0
 STATUS_NONFINITE = 1

@@ -239,6 +239,79 @@ __device__ __forceinline__ void red_shared_stats(uint32_t cnt_addr, uint32_t tic
 // removed afterwards, so the conversion costs one FADD and stays off the XU pipe.
 constexpr uint32_t TICK_BIAS = 0x4B000000u;
 
+// ---- memoised cumulative rows ---------------------------------------------------------------
+// The cumulative sums of a datum depend on its tick only, and residence times are small
+// integers with huge multiplicities (half of a typical slice holds fewer than a dozen distinct
+// ticks once the chain is in ascending-tick order).  Once per iteration the CTA therefore
+// computes the K cumulative sums for every tick value lo, lo+1, ... of its slice (up to
+// TABLE_FLOATS / KP rows) with exactly the per-datum arithmetic, and a quad whose ticks all fall
+// in that range reads its rows instead of recomputing them: the same bits, without the K
+// FFMA + MUFU + FADD per datum.  Quads beyond the table (the sparse tail) take the direct path.
+constexpr int TABLE_FLOATS = 4096;                          // 16 KB of shared memory per CTA
+__host__ __device__ constexpr int table_row_floats(int k) { return (k + 3) / 4 * 4; }
+
+struct TableView {
+    const float* rows;       // shared memory, row r = cumulative sums of tick lo + r
+    float limit;             // quads with every tick < limit are served from the table
+    uint32_t lo_bits;        // bits(lo + 2^23): row = bits(tick + 2^23) - lo_bits
+};
+
+template <int K, bool EXACT>
+__device__ __forceinline__ void build_table_row(float tick, const float2* __restrict__ s_coef, float* __restrict__ row)
+{
+    constexpr int KP = table_row_floats(K);
+    float l[KP];
+    float cum = 0.0f;
+    if constexpr (EXACT) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float2 ca = s_coef[k];
+            l[k] = __fsub_rn(ca.x, __fmul_rn(ca.y, tick));
+            m = fmaxf(m, l[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            cum = __fadd_rn(cum, soft_exp2(__fsub_rn(l[k], m)));
+            l[k] = cum;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float2 ca = s_coef[k];
+            cum += fast_exp2(fmaf(-ca.y, tick, ca.x));
+            l[k] = cum;
+        }
+    }
+#pragma unroll
+    for (int k = K; k < KP; ++k) l[k] = cum;
+#pragma unroll
+    for (int k = 0; k < KP; k += 4)
+        *reinterpret_cast<float4*>(row + k) = make_float4(l[k], l[k + 1], l[k + 2], l[k + 3]);
+}
+
+// label of one datum from its memoised row; returns true if the row underflowed (FAST only)
+template <int K>
+__device__ __forceinline__ bool label_from_table(float tick, float f12, const TableView& tab, int kmax, int& lab)
+{
+    constexpr int KP = table_row_floats(K);
+    const uint32_t r = __float_as_uint(tick + 8388608.0f) - tab.lo_bits;
+    const float4* const rp = reinterpret_cast<const float4*>(tab.rows + (size_t)r * KP);
+    float cum[K];
+#pragma unroll
+    for (int k4 = 0; k4 < KP / 4; ++k4) {
+        const float4 v = rp[k4];
+        if (4 * k4 + 0 < K) cum[4 * k4 + 0] = v.x;
+        if (4 * k4 + 1 < K) cum[4 * k4 + 1] = v.y;
+        if (4 * k4 + 2 < K) cum[4 * k4 + 2] = v.z;
+        if (4 * k4 + 3 < K) cum[4 * k4 + 3] = v.w;
+    }
+    const float total = cum[K - 1];
+    const float thr = __fmaf_rn(f12, total, -total);
+    lab = min(count_le<K>(cum, thr), kmax);
+    return !(total > 8.0779357e-28f);
+}
+
 // One quad (4 data) of the sweep: labels, statistics, optional label store.
 //
 // Statistics: shared-memory atomics for every label except the currently dominant one
@@ -248,22 +321,29 @@ constexpr uint32_t TICK_BIAS = 0x4B000000u;
 template <int K, bool EXACT, bool SAVE>
 __device__ __forceinline__ void sweep_quad(const float4 tk, const float4 f12, const float2* __restrict__ s_coef,
                                            int kmax, int dom, int i0, int n_data, bool partial,
-                                           uint32_t stat_addr, uint8_t* ind_row, const int32_t* __restrict__ perm)
+                                           uint32_t stat_addr, uint8_t* ind_row, const int32_t* __restrict__ perm,
+                                           const TableView& tab)
 {
     constexpr int D = data_in_flight(K);
     const float tks[4] = {tk.x, tk.y, tk.z, tk.w};
     const float fs[4] = {f12.x, f12.y, f12.z, f12.w};      // uniforms as floats in [1,2)
     int labs[4];
     unsigned redo = 0u;
+    if (!partial && fmaxf(fmaxf(tk.x, tk.y), fmaxf(tk.z, tk.w)) < tab.limit) {
 #pragma unroll
-    for (int h = 0; h < 4; h += D) {
-        float td[D], fd[D];
-        int ld[D];
+        for (int d = 0; d < 4; ++d)                        // memoised rows: same bits as the direct path
+            if (label_from_table<K>(tks[d], fs[d], tab, kmax, labs[d])) redo |= 1u << d;
+    } else {
 #pragma unroll
-        for (int d = 0; d < D; ++d) { td[d] = tks[h + d]; fd[d] = fs[h + d]; }
-        redo |= draw_labels<K, D, EXACT>(td, fd, s_coef, kmax, ld) << h;
+        for (int h = 0; h < 4; h += D) {
+            float td[D], fd[D];
+            int ld[D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) labs[h + d] = ld[d];
+            for (int d = 0; d < D; ++d) { td[d] = tks[h + d]; fd[d] = fs[h + d]; }
+            redo |= draw_labels<K, D, EXACT>(td, fd, s_coef, kmax, ld) << h;
+#pragma unroll
+            for (int d = 0; d < D; ++d) labs[h + d] = ld[d];
+        }
     }
     if (redo) {                                            // cold: after the quad, few registers are live
 #pragma unroll
@@ -291,7 +371,7 @@ __device__ __forceinline__ void sweep_slice(const float4* __restrict__ s_tick4, 
                                             int nq, int qb, int n_data, int kmax, int dom, uint32_t j,
                                             uint32_t chain_id, const RoundKeys& rk,
                                             const float4* __restrict__ u_row, uint32_t stat_addr,
-                                            uint8_t* ind_row, const int32_t* __restrict__ perm)
+                                            uint8_t* ind_row, const int32_t* __restrict__ perm, const TableView& tab)
 {
     // at most one quad of the whole chain is partial; find out once whether it is in this slice
     const int tail_q = ((n_data & 3) != 0) ? (n_data >> 2) - qb : -1;
@@ -306,7 +386,7 @@ __device__ __forceinline__ void sweep_slice(const float4* __restrict__ s_tick4, 
             f12 = make_float4(word_to_12(w.x), word_to_12(w.y), word_to_12(w.z), word_to_12(w.w));
         }
         sweep_quad<K, EXACT, SAVE>(tk, f12, s_coef, kmax, dom, (qb + q) * 4, n_data, q == tail_q,
-                                   stat_addr, ind_row, perm);
+                                   stat_addr, ind_row, perm, tab);
     }
 }
 
@@ -358,6 +438,8 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
     unsigned* const s_cnt = s_stat;
     unsigned* const s_sum = s_stat + 32;
     uint32_t stat_addr = (uint32_t)__cvta_generic_to_shared(s_stat);
+    __shared__ __align__(16) float s_table[TABLE_FLOATS];  // memoised cumulative rows of the running iteration
+    __shared__ unsigned s_red_lo[WARPS], s_red_hi[WARPS];  // smallest / largest tick of the slice
     __shared__ unsigned long long s_red_t[WARPS];
     __shared__ unsigned s_red_n[WARPS];
     __shared__ int s_dom;
@@ -402,7 +484,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
         const size_t u_pitch = (size_t)((n_data + 3) / 4) * 4;
 
         // ---- stage the slice: integer ticks -> float32 in shared memory -----------------
-        unsigned my_n = 0;
+        unsigned my_n = 0, my_lo = 0xffffffffu, my_hi = 0u;
         unsigned long long my_t = 0;
         for (int q = tid; q < nq; q += THREADS) {
             const int i0 = (qb + q) * 4;
@@ -416,6 +498,10 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
                     static_cast<const uint32_t*>(b.ticks) + tick_off)[qb + q];
                 t0 = raw.x; t1 = raw.y; t2 = raw.z; t3 = raw.w;
             }
+            if (i0 + 3 < n_data) {                           // full quads only: the partial quad never uses the table
+                my_lo = min(my_lo, min(min(t0, t1), min(t2, t3)));
+                my_hi = max(my_hi, max(max(t0, t1), max(t2, t3)));
+            }
             if (i0 + 0 >= n_data) t0 = 0;
             if (i0 + 1 >= n_data) t1 = 0;
             if (i0 + 2 >= n_data) t2 = 0;
@@ -426,7 +512,9 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
         }
         my_n = __reduce_add_sync(FULL, my_n);
         my_t = warp_sum_u64(my_t);
-        if (lane == 0) { s_red_n[warp] = my_n; s_red_t[warp] = my_t; }
+        my_lo = __reduce_min_sync(FULL, my_lo);
+        my_hi = __reduce_max_sync(FULL, my_hi);
+        if (lane == 0) { s_red_n[warp] = my_n; s_red_t[warp] = my_t; s_red_lo[warp] = my_lo; s_red_hi[warp] = my_hi; }
         if (tid < 32) {
             float2 ca = make_float2(-INFINITY, 0.0f);
             if (tid < kreal && !inject_coef)
@@ -453,6 +541,18 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
             rh_a = b.rhyper[((size_t)r * kreal + lane) * 2 + 0];
             rh_b = b.rhyper[((size_t)r * kreal + lane) * 2 + 1];
         }
+        // memoised rows cover ticks lo .. lo + table_rows - 1 of this slice
+        constexpr int KP = table_row_floats(K);
+        unsigned tick_lo = 0xffffffffu, tick_hi = 0u;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) { tick_lo = min(tick_lo, s_red_lo[w]); tick_hi = max(tick_hi, s_red_hi[w]); }
+        int table_rows = 0;
+        if (!(b.flags & BRTA_FLAG_NO_TABLE) && tick_lo <= tick_hi)
+            table_rows = (int)min((unsigned)(TABLE_FLOATS / KP), tick_hi - tick_lo + 1u);
+        TableView tab;
+        tab.rows = s_table;
+        tab.limit = table_rows > 0 ? (float)(tick_lo + (unsigned)table_rows) : -1.0f;
+        tab.lo_bits = __float_as_uint((float)tick_lo + 8388608.0f);
         unsigned char* const exch = static_cast<unsigned char*>(b.exchange) + b.exch_offset[r];
         // mailbox layout: slot[parity][member][32] of {tag<<32 | n_k, tag<<32 | tick sum}
         ulonglong2* const mbox = reinterpret_cast<ulonglong2*>(exch);
@@ -473,6 +573,11 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
                 }
                 __syncthreads();
             }
+            if (table_rows > 0) {                          // cumulative rows of this iteration's coefficients
+                for (int rr = tid; rr < table_rows; rr += THREADS)
+                    build_table_row<K, EXACT>((float)(tick_lo + (unsigned)rr), s_coef, s_table + (size_t)rr * KP);
+                __syncthreads();
+            }
             const bool save = (j % thin == 0);
             const int row = j / thin - 1;
             const float4* const u_row = inject_u
@@ -483,10 +588,10 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
             // ---- indicator draws + sufficient statistics (gibbs.py:196-207) -------------
             if (save)
                 sweep_slice<K, EXACT, true>(s_tick4, s_coef, nq, qb, n_data, kreal - 1, dom, (uint32_t)j, chain_id,
-                                            prm.rk, u_row, stat_addr, ind_base + (size_t)row * ind_stride, perm);
+                                            prm.rk, u_row, stat_addr, ind_base + (size_t)row * ind_stride, perm, tab);
             else
                 sweep_slice<K, EXACT, false>(s_tick4, s_coef, nq, qb, n_data, kreal - 1, dom, (uint32_t)j, chain_id,
-                                             prm.rk, u_row, stat_addr, nullptr, nullptr);
+                                             prm.rk, u_row, stat_addr, nullptr, nullptr, tab);
             PHASE_MARK(0);                                 // sweep
             __syncthreads();
             PHASE_MARK(1);                                 // wait for the CTA's slowest warp

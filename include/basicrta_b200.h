@@ -50,6 +50,8 @@ extern "C" {
 #define BRTA_FLAG_INJECT_COEF  2u   /* teacher forcing: per-iteration (coef_c, coef_a) rows given  */
 #define BRTA_FLAG_INJECT_U     4u   /* indicator uniforms given instead of the Philox stream       */
 #define BRTA_FLAG_TRACE        8u   /* write (n_k, sum tick_k) of every iteration                  */
+#define BRTA_FLAG_NO_TABLE    16u   /* recompute every datum's cumulative row instead of sharing the
+                                       rows of equal ticks (same results; for tests / measurements) */
 
 /* argument errors */
 #define BRTA_E_NULL      -1

@@ -117,3 +117,18 @@ def test_fast_mode_underflow_takes_the_safe_path(engine):
     assert np.abs(out['fast'].trace_nk - out['exact'].trace_nk).max() <= 4
     big = ticks > 200                                      # every term below 2^-126 without the max
     assert big.sum() > 3000 and np.all(out['fast'].indicator[0][big] == 2)
+
+
+@pytest.mark.parametrize('K', [3, 15, 30])
+def test_memoised_rows_are_bit_identical_to_recomputation(engine, K):
+    """Sharing the cumulative rows of equal ticks is a pure memoisation: free-running FAST chains
+    with and without the table produce identical weights, rates and labels."""
+    times = O.synth_times(30000, [0.7, 0.2, 0.1], [5, 0.3, 0.004], seed=12)
+    ticks = O.to_ticks(times, 0.1)
+    chains = [ChainInput(ticks=ticks, ts=0.1, chain_id=7), ChainInput(ticks=ticks[:1237], ts=0.1, chain_id=8)]
+    a = engine.run(chains, K, 400, thin=50, seed=21)
+    b = engine.run(chains, K, 400, thin=50, seed=21, flags=_cabi.FLAG_NO_TABLE)
+    for x, y in zip(a, b):
+        assert x.status == 0 and y.status == 0
+        assert np.array_equal(x.mcrates, y.mcrates) and np.array_equal(x.mcweights, y.mcweights)
+        assert np.array_equal(x.indicator, y.indicator)

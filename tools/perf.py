@@ -16,6 +16,7 @@ from basicrta_b200.engine import ChainInput, GibbsEngine  # noqa: E402
 
 n_chains, niter = int(sys.argv[1]), int(sys.argv[2])
 nd = [int(a) for a in sys.argv[3:] if a.isdigit()]
+print('NO TABLE' if 'notable' in sys.argv else 'table', end=' ')
 if nd:
     rng = np.random.default_rng(1)
     ticks = []
@@ -29,7 +30,8 @@ chains = [ChainInput(ticks=t, ts=0.1, chain_id=i) for i, t in enumerate(ticks)]
 cps = os.environ.get('BRTA_CTAS_PER_SM')
 nw = os.environ.get('BRTA_WAVES')
 eng = GibbsEngine(0, ctas_per_sm=int(cps) if cps else None)
-db = eng.prepare(chains, 15, niter, thin=100, seed=1, n_waves=int(nw) if nw else None)
+db = eng.prepare(chains, 15, niter, thin=100, seed=1, n_waves=int(nw) if nw else None,
+                 flags=_cabi.FLAG_NO_TABLE if 'notable' in sys.argv else 0)
 p = db.plan
 best = 1e30
 for rep in range(3):
