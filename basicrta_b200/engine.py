@@ -26,6 +26,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _cabi
+from .memo import ChainCost
 from .plan import build_plan
 
 LOG2E = 1.4426950408889634
@@ -127,7 +128,9 @@ class GibbsEngine:
         self.overhead_quads = overhead_quads
 
     # ---- schedule ----------------------------------------------------------------------
-    def _plan(self, n_data, ncomp, flags, n_waves=None):
+    def _plan(self, n_data, ncomp, flags, n_waves=None, costs=None):
+        """``costs``: per chain a :class:`memo.ChainCost` (ticks in canonical order) -- slices are then
+        cut to equal time under the memoised-row cost model instead of equal length."""
         n_quads = (np.asarray(n_data, dtype=np.int64) + 3) // 4
         # occupancy is set by registers for small slices; ask with a small slice first,
         # then shrink the capacity to what that occupancy leaves per CTA.
@@ -139,7 +142,14 @@ class GibbsEngine:
         cap = (smem_sm // per_sm - info.static_smem - 1024) // 16
         grid = self.caps.sm_count * per_sm
         kw = {} if self.overhead_quads is None else {'overhead_quads': self.overhead_quads}
-        plan = build_plan(n_quads, grid, cap, n_waves=n_waves, **kw)
+        if costs is None:
+            plan = build_plan(n_quads, grid, cap, n_waves=n_waves, **kw)
+        else:
+            # pass 1 (equal quads) fixes provisional team sizes; pass 2 balances time with the cost model
+            first = build_plan(n_quads, grid, cap, n_waves=n_waves, **kw)
+            cost = [costs[r].total_cost(int(first.team_size[r]), cap) for r in range(len(n_quads))]
+            plan = build_plan(n_quads, grid, cap, n_waves=n_waves, cost=cost,
+                              splitter=lambda r, c: costs[r].split(c, cap), **kw)
         check = _cabi.launch_info(self.device, ncomp, flags, plan.slice_cap_quads)
         if check.ctas_per_sm < per_sm:
             raise _cabi.BrtaError('schedule assumes more co-resident CTAs than the device grants')
@@ -171,6 +181,8 @@ class GibbsEngine:
             raise ValueError('ticks must lie in [0, 2^23)')
         tick_dtype = np.uint16 if max_tick < 65536 else np.uint32
 
+        # canonical order: ascending ticks (stable).  Philox word p belongs to canonical position p.
+        order = [np.argsort(np.asarray(ch.ticks), kind='stable').astype(np.int32) for ch in chains]
         if shard is not None:
             if R != 1:
                 raise ValueError('a sharded launch holds exactly one chain')
@@ -182,7 +194,10 @@ class GibbsEngine:
         else:
             d0 = 0
             n_local = n_data
-            plan = self._plan(n_data, K, flags, n_waves=n_waves)
+            costs = None
+            if not flags & _cabi.FLAG_NO_TABLE:
+                costs = [ChainCost(np.asarray(ch.ticks)[o], K) for ch, o in zip(chains, order)]
+            plan = self._plan(n_data, K, flags, n_waves=n_waves, costs=costs)
         if int(plan.team_size.max()) * int(niter) >= (1 << 31):
             raise ValueError('team_size * niter overflows the arrive counter')
 
@@ -196,8 +211,6 @@ class GibbsEngine:
         init_c = np.zeros((R, K), dtype=np.float32)
         init_a = np.zeros((R, K), dtype=np.float32)
         w0, r0 = initial_state(K)
-        # canonical order: ascending ticks (stable).  Philox word p belongs to canonical position p.
-        order = [np.argsort(np.asarray(ch.ticks), kind='stable').astype(np.int32) for ch in chains]
         for r, ch in enumerate(chains):
             t = np.asarray(ch.ticks)[order[r]][d0:d0 + int(n_local[r])]
             ticks[tick_offset[r] + d0:tick_offset[r] + d0 + len(t)] = t

@@ -67,7 +67,7 @@ def _allocate_wave(quads, cmin, grid):
     return team, dmax
 
 
-def _assign_ctas(n_quads, order, groups, alloc, grid, overhead_quads):
+def _assign_ctas(n_quads, cost_q, order, groups, alloc, grid, overhead_quads, splitter):
     """Gang list-scheduling of the teams on the CTAs.  CTAs never synchronise between waves,
     so a CTA that finishes its wave-w task early can start its wave-(w+1) task early: within a
     wave the teams with the longest slices take the CTAs that become free first, which absorbs
@@ -80,8 +80,8 @@ def _assign_ctas(n_quads, order, groups, alloc, grid, overhead_quads):
     per_cta = [[] for _ in range(grid)]
     free_at = np.zeros(grid, dtype=np.float64)
     for w, ((a, b), team) in enumerate(zip(groups, alloc)):
-        members = [(int(order[a + i]), int(c)) for i, c in enumerate(team)]
-        slice_len = {r: -(-int(n_quads[r]) // c) for r, c in members}
+        members = [(int(order[a + i]), min(int(c), int(n_quads[int(order[a + i])]))) for i, c in enumerate(team)]
+        slice_len = {r: -(-int(cost_q[r]) // c) for r, c in members}
         members.sort(key=lambda rc: -slice_len[rc[0]])
         avail = list(np.argsort(free_at, kind='stable'))         # earliest-free CTAs first
         pos = 0
@@ -90,13 +90,17 @@ def _assign_ctas(n_quads, order, groups, alloc, grid, overhead_quads):
             pos += c
             q = int(n_quads[r])
             team_size[r], wave_of[r] = c, w
-            base, rem = divmod(q, c)
+            if splitter is None:
+                base, rem = divmod(q, c)
+                bounds = [rank * base + min(rank, rem) for rank in range(c + 1)]
+            else:
+                bounds = [int(x) for x in splitter(r, c)]
+                assert len(bounds) == c + 1 and bounds[0] == 0 and bounds[-1] == q
             start = max(free_at[x] for x in ctas)
-            begin = 0
             for rank, x in enumerate(ctas):
-                cnt = base + (1 if rank < rem else 0)
-                per_cta[int(x)].append((r, c, rank, begin, cnt, w))
-                begin += cnt
+                cnt = bounds[rank + 1] - bounds[rank]
+                assert cnt >= 1
+                per_cta[int(x)].append((r, c, rank, bounds[rank], cnt, w))
                 free_at[x] = start + slice_len[r] + overhead_quads
         assert pos <= grid
     return team_size, wave_of, per_cta, float(free_at.max())
@@ -119,10 +123,17 @@ def _group_contiguous(quads_sorted, cmin_sorted, n_waves, grid):
     return groups
 
 
-def build_plan(n_quads, grid, cap_quads, overhead_quads=DEFAULT_OVERHEAD_QUADS, n_waves=None):
+def build_plan(n_quads, grid, cap_quads, overhead_quads=DEFAULT_OVERHEAD_QUADS, n_waves=None,
+               cost=None, splitter=None):
     """Schedule chains with ``n_quads[r]`` quads (4 data each) on ``grid`` CTAs whose shared
-    memory holds at most ``cap_quads`` quads."""
+    memory holds at most ``cap_quads`` quads.
+
+    ``cost[r]`` (optional, in quad-times) is what the time balance uses instead of the quad
+    count -- quads served from the memoised rows are cheaper than recomputed ones -- and
+    ``splitter(r, c)`` (optional) returns the c+1 quad boundaries of chain r's slices; the
+    default cuts equal quad counts."""
     n_quads = np.asarray(n_quads, dtype=np.int64)
+    cost_q = n_quads if cost is None else np.maximum(1, np.rint(np.asarray(cost, dtype=np.float64))).astype(np.int64)
     R = len(n_quads)
     if R == 0:
         raise ValueError('empty batch')
@@ -133,8 +144,8 @@ def build_plan(n_quads, grid, cap_quads, overhead_quads=DEFAULT_OVERHEAD_QUADS, 
     if cmin.max() > grid:
         raise ValueError(f'a chain needs {int(cmin.max())} CTAs of {cap_quads} quads; grid has {grid}')
 
-    order = np.argsort(-n_quads, kind='stable')
-    qs, cs = n_quads[order], cmin[order]
+    order = np.argsort(-cost_q, kind='stable')
+    qs, cs = cost_q[order], cmin[order]
     w_min = max(1, -(-R // grid), -(-int(cs.sum()) // grid))
     if n_waves is not None:
         candidates = [max(int(n_waves), w_min)]
@@ -146,12 +157,13 @@ def build_plan(n_quads, grid, cap_quads, overhead_quads=DEFAULT_OVERHEAD_QUADS, 
     for W in candidates:
         groups = _group_contiguous(qs, cs, W, grid)
         alloc = [_allocate_wave(qs[a:b], cs[a:b], grid)[0] for (a, b) in groups]
-        cost = _assign_ctas(n_quads, order, groups, alloc, grid, overhead_quads)[3]
-        if best is None or cost < best[0] - 1e-9:
-            best = (cost, groups, alloc)
-    cost, groups, alloc = best
+        span = _assign_ctas(n_quads, cost_q, order, groups, alloc, grid, overhead_quads, None)[3]
+        if best is None or span < best[0] - 1e-9:
+            best = (span, groups, alloc)
+    span, groups, alloc = best
 
-    team_size, wave_of, per_cta, makespan = _assign_ctas(n_quads, order, groups, alloc, grid, overhead_quads)
+    team_size, wave_of, per_cta, makespan = _assign_ctas(n_quads, cost_q, order, groups, alloc, grid,
+                                                         overhead_quads, splitter)
 
     flat, begin = [], np.zeros(grid + 1, dtype=np.int32)
     for bidx, lst in enumerate(per_cta):
@@ -161,7 +173,7 @@ def build_plan(n_quads, grid, cap_quads, overhead_quads=DEFAULT_OVERHEAD_QUADS, 
     return Plan(tasks=tasks, cta_task_begin=begin, grid=grid,
                 slice_cap_quads=int(tasks['quad_count'].max()), n_waves=len(groups),
                 team_size=team_size, wave_of_chain=wave_of,
-                est_efficiency=float(n_quads.sum()) / (grid * max(makespan, 1.0)))
+                est_efficiency=float(cost_q.sum()) / (grid * max(makespan, 1.0)))
 
 
 def shard_chains(costs, n_shards):
