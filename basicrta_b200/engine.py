@@ -110,6 +110,7 @@ class DeviceBatch:
     flags: int = 0
     h2d_bytes: int = 0
     units: float = 0.0                                # sum_r N_r * K * niter
+    executed_ex2_share: float = 1.0                   # ex2 actually executed / units (memoised rows make it < 1)
 
 
 class GibbsEngine:
@@ -312,11 +313,24 @@ class GibbsEngine:
             b.trace_tk = dev_zeros('trace_tk', (R, niter, K), torch.int64)
 
         torch.cuda.current_stream(dev).synchronize()
+        ex2_share = 1.0
+        if shard is None and costs is not None:
+            done = 0.0
+            for task in plan.tasks:
+                cc = costs[int(task['chain'])]
+                s0, e0 = int(task['quad_begin']), int(task['quad_begin'] + task['quad_count'])
+                k = cc.served(s0, e0)
+                rows_built = 0
+                if k > 0:
+                    hi_tick = int(cc.qmax[min(e0, cc.n_full) - 1]) if min(e0, cc.n_full) > s0 else int(cc.qmin[s0])
+                    rows_built = min(cc.rows, hi_tick - int(cc.qmin[s0]) + 1)
+                done += 4.0 * (e0 - s0 - k) + rows_built
+            ex2_share = done / float(n_data.sum())
         if shard is not None:
             n_data, ind_offset = n_local, ind_offset + d0            # host-side views are shard-local
         return DeviceBatch(batch=b, plan=plan, tensors=T, host=H, order=order, n_data=n_data, ind_offset=ind_offset,
                            rows=rows, ncomp=K, niter=int(niter), flags=int(flags), h2d_bytes=h2d,
-                           units=float(n_data.sum()) * K * int(niter))
+                           units=float(n_data.sum()) * K * int(niter), executed_ex2_share=ex2_share)
 
     # ---- run -----------------------------------------------------------------------------
     def reset(self, db):

@@ -111,11 +111,11 @@ def run_reference_arm(args):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3, 'higher_is_better': True,
         'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'C2 full-membrane sweep: 400 residues x 1e4-1e5 times, ncomp=15, niter=110000 '
-                               '(bounded sample, see cpu_baseline.sample)'},
+        'config': {'workload': f'C2 full-membrane sweep: {N_RESIDUES} residues x 1e4-1e5 times, ncomp={NCOMP}, '
+                               f'niter={NITER}, thin={THIN} (CPU arm: bounded sample of it, see cpu_baseline.sample)'},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'residues_per_hour': n_chains * (NITER / niter) ** -1 * 3600.0 / sec,
+        'residues_per_hour': n_chains * (niter / NITER) * 3600.0 / sec,
     }))
 
 
@@ -307,8 +307,11 @@ def run_b200_arm(args):
             'gpu_launches': args.steps * world,
             'roofline': {'bound': 'mufu', 'achieved': per_gpu / 1e9, 'peak': peak / 1e9, 'unit': 'G ex2/s',
                          'frac': per_gpu / peak, 'traffic': None,
-                         'note': 'per GPU; 1 MUFU.EX2 per (datum, component) pair per iteration (SURVEY 8d); peak = '
-                                 'brta_mufu_probe measured in this run (nominal 148 SM x 16/clk x 1.965 GHz = 4654 G/s)',
+                         'executed_ex2_share': db.executed_ex2_share,
+                         'note': 'per GPU; algorithmic unit = 1 ex2 per (datum, component) pair per iteration (SURVEY 8d); '
+                                 'peak = brta_mufu_probe measured in this run (nominal 148 SM x 16/clk x 1.965 GHz = 4654 G/s). '
+                                 'Data with equal ticks share memoised cumulative rows, so only executed_ex2_share of the '
+                                 'algorithmic ex2 are issued to the XU pipe (rank 0 figure); frac counts algorithmic units.',
                          'hbm': {'achieved': algo_bytes / sec / 1e9, 'peak': hbm, 'unit': 'GB/s',
                                  'frac': algo_bytes / sec / 1e9 / hbm,
                                  'note': 'algorithmic bytes = ticks in (2 B/datum) + labels out (1 B/datum/saved row); '

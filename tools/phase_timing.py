@@ -44,3 +44,23 @@ print(f'{ms:.2f} ms, {db.units / ms / 1e6:.1f} G units/s, grid {db.plan.grid}, t
       f'slice {db.plan.slice_cap_quads} quads; cycles/iter {tot / niter:.0f}')
 for i, nme in enumerate(names):
     print(f'  {nme:14s} {ph[:, i].mean() / niter:9.0f} cyc/iter  {100 * ph[:, i].mean() / tot:5.1f} %   (min {ph[:, i].min() / niter:.0f} max {ph[:, i].max() / niter:.0f})')
+
+# regression: sweep cycles per iteration of a CTA ~ a * served quads + b * recomputed quads + c * tasks
+try:
+    from basicrta_b200.memo import ChainCost
+    srt = [np.sort(np.asarray(c.ticks)) for c in chains]
+    costs = [ChainCost(t, K) for t in srt]
+    A = np.zeros((db.plan.grid, 3))
+    for bidx in range(db.plan.grid):
+        for t in db.plan.tasks_of_cta(bidx):
+            s0, e0 = int(t['quad_begin']), int(t['quad_begin'] + t['quad_count'])
+            k = costs[int(t['chain'])].served(s0, e0)
+            A[bidx] += (k, e0 - s0 - k, 1)
+    full = buf.cpu().numpy().reshape(-1, 8).astype(np.float64)
+    y = full[:, 0] / niter
+    sel = A[:, 2] > 0
+    coef, *_ = np.linalg.lstsq(A[sel], y[sel], rcond=None)
+    print(f'sweep cycles/iter ~ {coef[0]:.2f} * served + {coef[1]:.2f} * recomputed + {coef[2]:.0f} * tasks  '
+          f'(ratio served/recomputed = {coef[0] / coef[1]:.3f}); served share {A[:, 0].sum() / A[:, :2].sum():.3f}')
+except Exception as e:
+    print('regression failed:', e)
