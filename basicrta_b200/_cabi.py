@@ -67,7 +67,7 @@ class Batch(C.Structure):
         ('n_chains', C.c_int32), ('ncomp', C.c_int32), ('niter', C.c_int32), ('thin', C.c_int32),
         ('tick_bytes', C.c_int32), ('flags', C.c_uint32), ('seed', C.c_uint64),
         ('ticks', C.c_void_p), ('tick_offset', C.c_void_p), ('perm', C.c_void_p), ('perm_offset', C.c_void_p),
-        ('n_data', C.c_void_p),
+        ('n_data', C.c_void_p), ('max_tick', C.c_void_p),
         ('chain_id', C.c_void_p), ('ts', C.c_void_p), ('whyper', C.c_void_p),
         ('rhyper', C.c_void_p), ('init_c', C.c_void_p), ('init_a', C.c_void_p),
         ('mcweights', C.c_void_p), ('mcrates', C.c_void_p), ('indicator', C.c_void_p),

@@ -234,11 +234,6 @@ __device__ __forceinline__ void red_shared_stats(uint32_t cnt_addr, uint32_t tic
                  :: "r"(cnt_addr), "r"(tick_bits) : "memory");
 }
 
-// float tick + 2^23 has the integer tick in its mantissa: bits = 0x4B000000 + tick (exact for
-// tick < 2^23).  The accumulator adds these bits modulo 2^32 and the bias n * 0x4B000000 is
-// removed afterwards, so the conversion costs one FADD and stays off the XU pipe.
-constexpr uint32_t TICK_BIAS = 0x4B000000u;
-
 // ---- memoised cumulative rows ---------------------------------------------------------------
 // The cumulative sums of a datum depend on its tick only, and residence times are small
 // integers with huge multiplicities (half of a typical slice holds fewer than a dozen distinct
@@ -252,8 +247,8 @@ __host__ __device__ constexpr int table_row_floats(int k) { return (k + 3) / 4 *
 
 struct TableView {
     const float* rows;       // shared memory, row r = cumulative sums of tick lo + r
-    float limit;             // quads with every tick < limit are served from the table
-    uint32_t lo_bits;        // bits(lo + 2^23): row = bits(tick + 2^23) - lo_bits
+    uint32_t lo;             // first tick of the table
+    uint32_t limit;          // quads with every tick < limit are served from the table (0: no table)
 };
 
 template <int K, bool EXACT>
@@ -292,10 +287,10 @@ __device__ __forceinline__ void build_table_row(float tick, const float2* __rest
 
 // label of one datum from its memoised row; returns true if the row underflowed (FAST only)
 template <int K>
-__device__ __forceinline__ bool label_from_table(float tick, float f12, const TableView& tab, int kmax, int& lab)
+__device__ __forceinline__ bool label_from_table(uint32_t tick, float f12, const TableView& tab, int kmax, int& lab)
 {
     constexpr int KP = table_row_floats(K);
-    const uint32_t r = __float_as_uint(tick + 8388608.0f) - tab.lo_bits;
+    const uint32_t r = tick - tab.lo;
     const float4* const rp = reinterpret_cast<const float4*>(tab.rows + (size_t)r * KP);
     float cum[K];
 #pragma unroll
@@ -318,22 +313,31 @@ __device__ __forceinline__ bool label_from_table(float tick, float f12, const Ta
 // (`dom`, the most populated component of the previous iteration), whose statistics follow
 // by subtraction from the slice totals -- exact integer arithmetic, so any choice of `dom`
 // gives the same result; skipping it removes most of the same-address contention.
+// integer tick -> float32 without the XU pipe: 2^23 + tick is exact for tick < 2^23
+__device__ __forceinline__ float tick_to_float(uint32_t tick)
+{
+    return __uint_as_float(0x4B000000u | tick) - 8388608.0f;
+}
+
 template <int K, bool EXACT, bool SAVE>
-__device__ __forceinline__ void sweep_quad(const float4 tk, const float4 f12, const float2* __restrict__ s_coef,
+__device__ __forceinline__ void sweep_quad(const uint4 tk, const float4 f12, const float2* __restrict__ s_coef,
                                            int kmax, int dom, int i0, int n_data, bool partial,
                                            uint32_t stat_addr, uint8_t* ind_row, const int32_t* __restrict__ perm,
                                            const TableView& tab)
 {
     constexpr int D = data_in_flight(K);
-    const float tks[4] = {tk.x, tk.y, tk.z, tk.w};
+    const uint32_t tis[4] = {tk.x, tk.y, tk.z, tk.w};
+    float tks[4];
     const float fs[4] = {f12.x, f12.y, f12.z, f12.w};      // uniforms as floats in [1,2)
     int labs[4];
     unsigned redo = 0u;
-    if (!partial && fmaxf(fmaxf(tk.x, tk.y), fmaxf(tk.z, tk.w)) < tab.limit) {
+    if (!partial && max(max(tk.x, tk.y), max(tk.z, tk.w)) < tab.limit) {
 #pragma unroll
         for (int d = 0; d < 4; ++d)                        // memoised rows: same bits as the direct path
-            if (label_from_table<K>(tks[d], fs[d], tab, kmax, labs[d])) redo |= 1u << d;
+            if (label_from_table<K>(tis[d], fs[d], tab, kmax, labs[d])) redo |= 1u << d;
     } else {
+#pragma unroll
+        for (int d = 0; d < 4; ++d) tks[d] = tick_to_float(tis[d]);
 #pragma unroll
         for (int h = 0; h < 4; h += D) {
             float td[D], fd[D];
@@ -348,7 +352,7 @@ __device__ __forceinline__ void sweep_quad(const float4 tk, const float4 f12, co
     if (redo) {                                            // cold: after the quad, few registers are live
 #pragma unroll
         for (int d = 0; d < 4; ++d)
-            if (redo & (1u << d)) labs[d] = draw_label_safe<K>(tks[d], fs[d], s_coef, kmax);
+            if (redo & (1u << d)) labs[d] = draw_label_safe<K>(tick_to_float(tis[d]), fs[d], s_coef, kmax);
     }
     if (partial) {                                         // the chain's last quad: padding is never counted
 #pragma unroll
@@ -358,7 +362,7 @@ __device__ __forceinline__ void sweep_quad(const float4 tk, const float4 f12, co
 #pragma unroll
     for (int d = 0; d < 4; ++d)
         if (labs[d] != dom)                                // ATOMS cost scales with the active lanes
-            red_shared_stats(stat_addr + 4u * (uint32_t)labs[d], __float_as_uint(tks[d] + 8388608.0f));
+            red_shared_stats(stat_addr + 4u * (uint32_t)labs[d], tis[d]);
     if (SAVE) {                                            // 1 iteration in `thin`: dense [S,N] bytes
 #pragma unroll
         for (int d = 0; d < 4; ++d)
@@ -367,7 +371,8 @@ __device__ __forceinline__ void sweep_quad(const float4 tk, const float4 f12, co
 }
 
 template <int K, bool EXACT, bool SAVE>
-__device__ __forceinline__ void sweep_slice(const float4* __restrict__ s_tick4, const float2* __restrict__ s_coef,
+__device__ __forceinline__ void sweep_slice(const unsigned char* __restrict__ s_ticks, bool ticks16,
+                                            const float2* __restrict__ s_coef,
                                             int nq, int qb, int n_data, int kmax, int dom, uint32_t j,
                                             uint32_t chain_id, const RoundKeys& rk,
                                             const float4* __restrict__ u_row, uint32_t stat_addr,
@@ -376,7 +381,13 @@ __device__ __forceinline__ void sweep_slice(const float4* __restrict__ s_tick4, 
     // at most one quad of the whole chain is partial; find out once whether it is in this slice
     const int tail_q = ((n_data & 3) != 0) ? (n_data >> 2) - qb : -1;
     for (int q = threadIdx.x; q < nq; q += THREADS) {
-        const float4 tk = s_tick4[q];
+        uint4 tk;                                          // shared memory holds the ticks as stored: 8 or 16 B per quad
+        if (ticks16) {
+            const uint2 raw = reinterpret_cast<const uint2*>(s_ticks)[q];
+            tk = make_uint4(raw.x & 0xffffu, raw.x >> 16, raw.y & 0xffffu, raw.y >> 16);
+        } else {
+            tk = reinterpret_cast<const uint4*>(s_ticks)[q];
+        }
         float4 f12;
         if (u_row != nullptr) {
             const float4 uu = u_row[qb + q];
@@ -429,7 +440,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
 {
     const brta_batch& b = prm.b;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4* s_tick4 = reinterpret_cast<float4*>(smem_raw);
+
 
     __shared__ __align__(16) float2 s_coef[32];            // {coef_c, coef_a}
     // this CTA's statistics of the running iteration: [0..31] n_k, [32..63] biased tick sums
@@ -475,6 +486,8 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
         const bool sharded = n_shards > 1;                 // the chain continues on other GPUs
         const bool mailbox = !sharded && team > 1 && team <= BRTA_MAILBOX_MAX_TEAM;
         const uint32_t chain_id = b.chain_id[r];
+        // a chain whose largest tick fits 16 bits keeps its slice in shared memory at 8 B per quad
+        const bool ticks16 = b.max_tick[r] < 65536u;
         const float ts = b.ts[r];
         const int64_t tick_off = b.tick_offset[r];
         const int ind_stride = b.ind_stride[r];
@@ -508,7 +521,8 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
             if (i0 + 3 >= n_data) t3 = 0;
             my_n += (unsigned)min(4, max(0, n_data - i0));
             my_t += (unsigned long long)t0 + t1 + t2 + t3;
-            s_tick4[q] = make_float4((float)t0, (float)t1, (float)t2, (float)t3);
+            if (ticks16) reinterpret_cast<uint2*>(smem_raw)[q] = make_uint2(t0 | (t1 << 16), t2 | (t3 << 16));
+            else reinterpret_cast<uint4*>(smem_raw)[q] = make_uint4(t0, t1, t2, t3);
         }
         my_n = __reduce_add_sync(FULL, my_n);
         my_t = warp_sum_u64(my_t);
@@ -551,8 +565,8 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
             table_rows = (int)min((unsigned)(TABLE_FLOATS / KP), tick_hi - tick_lo + 1u);
         TableView tab;
         tab.rows = s_table;
-        tab.limit = table_rows > 0 ? (float)(tick_lo + (unsigned)table_rows) : -1.0f;
-        tab.lo_bits = __float_as_uint((float)tick_lo + 8388608.0f);
+        tab.lo = tick_lo;
+        tab.limit = table_rows > 0 ? tick_lo + (unsigned)table_rows : 0u;
         unsigned char* const exch = static_cast<unsigned char*>(b.exchange) + b.exch_offset[r];
         // mailbox layout: slot[parity][member][32] of {tag<<32 | n_k, tag<<32 | tick sum}
         ulonglong2* const mbox = reinterpret_cast<ulonglong2*>(exch);
@@ -587,10 +601,10 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
 
             // ---- indicator draws + sufficient statistics (gibbs.py:196-207) -------------
             if (save)
-                sweep_slice<K, EXACT, true>(s_tick4, s_coef, nq, qb, n_data, kreal - 1, dom, (uint32_t)j, chain_id,
+                sweep_slice<K, EXACT, true>(smem_raw, ticks16, s_coef, nq, qb, n_data, kreal - 1, dom, (uint32_t)j, chain_id,
                                             prm.rk, u_row, stat_addr, ind_base + (size_t)row * ind_stride, perm, tab);
             else
-                sweep_slice<K, EXACT, false>(s_tick4, s_coef, nq, qb, n_data, kreal - 1, dom, (uint32_t)j, chain_id,
+                sweep_slice<K, EXACT, false>(smem_raw, ticks16, s_coef, nq, qb, n_data, kreal - 1, dom, (uint32_t)j, chain_id,
                                              prm.rk, u_row, stat_addr, nullptr, nullptr, tab);
             PHASE_MARK(0);                                 // sweep
             __syncthreads();
@@ -599,7 +613,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
             // ---- this CTA's partials; the uncounted dominant label follows by subtraction --
             if (warp == 0) {
                 unsigned cnt = s_cnt[lane];
-                unsigned sum = s_sum[lane] - cnt * TICK_BIAS;   // remove the float-bits bias (mod 2^32)
+                unsigned sum = s_sum[lane];
                 s_cnt[lane] = 0;
                 s_sum[lane] = 0;
                 const unsigned oc = __reduce_add_sync(FULL, cnt);
@@ -957,6 +971,7 @@ int brta_gibbs_run_batch(const brta_batch* batch, void* stream)
         return brta::fail(BRTA_E_RANGE, "n_chains, niter, thin, grid_ctas, slice_cap_quads must be >= 1");
     if (b.tick_bytes != 2 && b.tick_bytes != 4)
         return brta::fail(BRTA_E_RANGE, "tick_bytes must be 2 or 4");
+    if (!b.max_tick) return brta::fail(BRTA_E_NULL, "max_tick is required");
     if (!b.ticks || !b.tick_offset || !b.n_data || !b.chain_id || !b.ts || !b.whyper || !b.rhyper ||
         !b.indicator || !b.ind_offset || !b.ind_stride || !b.status || !b.tasks ||
         !b.cta_task_begin || !b.exchange || !b.exch_offset)

@@ -129,9 +129,10 @@ class GibbsEngine:
         self.overhead_quads = overhead_quads
 
     # ---- schedule ----------------------------------------------------------------------
-    def _plan(self, n_data, ncomp, flags, n_waves=None, costs=None):
+    def _plan(self, n_data, ncomp, flags, n_waves=None, costs=None, narrow=None):
         """``costs``: per chain a :class:`memo.ChainCost` (ticks in canonical order) -- slices are then
-        cut to equal time under the memoised-row cost model instead of equal length."""
+        cut to equal time under the memoised-row cost model instead of equal length.  ``narrow[r]``:
+        chain r's ticks fit 16 bits, so its slices take 8 B per quad of shared memory instead of 16."""
         n_quads = (np.asarray(n_data, dtype=np.int64) + 3) // 4
         # occupancy is set by registers for small slices; ask with a small slice first,
         # then shrink the capacity to what that occupancy leaves per CTA.
@@ -140,7 +141,9 @@ class GibbsEngine:
         if per_sm < 1:
             raise _cabi.BrtaError('sampler kernel does not fit on an SM')
         smem_sm = 227 * 1024
-        cap = (smem_sm // per_sm - info.static_smem - 1024) // 16
+        cap16 = (smem_sm // per_sm - info.static_smem - 1024) // 16          # 16-byte units per CTA
+        narrow = np.zeros(len(n_quads), bool) if narrow is None else np.asarray(narrow, bool)
+        cap = np.where(narrow, 2 * cap16, cap16).astype(np.int64)             # quads per CTA, per chain
         grid = self.caps.sm_count * per_sm
         kw = {} if self.overhead_quads is None else {'overhead_quads': self.overhead_quads}
         if costs is None:
@@ -148,10 +151,13 @@ class GibbsEngine:
         else:
             # pass 1 (equal quads) fixes provisional team sizes; pass 2 balances time with the cost model
             first = build_plan(n_quads, grid, cap, n_waves=n_waves, **kw)
-            cost = [costs[r].total_cost(int(first.team_size[r]), cap) for r in range(len(n_quads))]
+            cost = [costs[r].total_cost(int(first.team_size[r]), int(cap[r])) for r in range(len(n_quads))]
             plan = build_plan(n_quads, grid, cap, n_waves=n_waves, cost=cost,
-                              splitter=lambda r, c: costs[r].split(c, cap), **kw)
-        check = _cabi.launch_info(self.device, ncomp, flags, plan.slice_cap_quads)
+                              splitter=lambda r, c: costs[r].split(c, int(cap[r])), **kw)
+        # dynamic shared memory in 16-byte units: the largest task slice
+        units = np.where(narrow[plan.tasks['chain']], (plan.tasks['quad_count'] + 1) // 2, plan.tasks['quad_count'])
+        plan.smem_units = int(units.max())
+        check = _cabi.launch_info(self.device, ncomp, flags, plan.smem_units)
         if check.ctas_per_sm < per_sm:
             raise _cabi.BrtaError('schedule assumes more co-resident CTAs than the device grants')
         return plan
@@ -190,7 +196,7 @@ class GibbsEngine:
             sq0, snq = int(shard['quad_begin']), int(shard['quad_count'])
             d0 = 4 * sq0                                              # first datum of this GPU's shard
             n_local = np.array([min(int(n_data[0]), 4 * (sq0 + snq)) - d0], dtype=np.int64)
-            plan = self._plan(np.array([4 * snq]), K, flags, n_waves=n_waves)
+            plan = self._plan(np.array([4 * snq]), K, flags, n_waves=n_waves, narrow=[max_tick < 65536])
             plan.tasks['quad_begin'] += sq0                          # tasks carry GLOBAL quad indices
         else:
             d0 = 0
@@ -198,7 +204,8 @@ class GibbsEngine:
             costs = None
             if not flags & _cabi.FLAG_NO_TABLE:
                 costs = [ChainCost(np.asarray(ch.ticks)[o], K) for ch, o in zip(chains, order)]
-            plan = self._plan(n_data, K, flags, n_waves=n_waves, costs=costs)
+            plan = self._plan(n_data, K, flags, n_waves=n_waves, costs=costs,
+                              narrow=[int(np.max(ch.ticks)) < 65536 for ch in chains])
         if int(plan.team_size.max()) * int(niter) >= (1 << 31):
             raise ValueError('team_size * niter overflows the arrive counter')
 
@@ -262,6 +269,7 @@ class GibbsEngine:
             b.perm = up('perm', np.concatenate(order))
             b.perm_offset = up('perm_offset', perm_offset)
         b.n_data = up('n_data', n_data.astype(np.int32))
+        b.max_tick = up('max_tick', np.array([int(np.max(ch.ticks)) for ch in chains], dtype=np.int64).astype(np.int32))
         b.chain_id = up('chain_id', chain_id.view(np.int32))
         b.ts = up('ts', ts)
         b.whyper = up('whyper', whyper)
@@ -273,7 +281,7 @@ class GibbsEngine:
         b.tasks = up('tasks', plan.tasks.view(np.int32).reshape(-1, 6))
         b.cta_task_begin = up('cta_task_begin', plan.cta_task_begin)
         b.grid_ctas = plan.grid
-        b.slice_cap_quads = plan.slice_cap_quads
+        b.slice_cap_quads = plan.smem_units
 
         def dev_zeros(name, shape, dtype):
             T[name] = torch.zeros(shape, dtype=dtype, device=dev)

@@ -37,7 +37,8 @@ class Plan:
     n_waves: int
     team_size: np.ndarray        # int32 [R]
     wave_of_chain: np.ndarray    # int32 [R]
-    est_efficiency: float        # sum(quads) / (grid * sum_w max slice)
+    est_efficiency: float        # sum(cost) / (grid * simulated makespan)
+    smem_units: int = 0          # dynamic shared memory per CTA in 16-byte units; set by the engine
 
     def tasks_of_cta(self, b):
         return self.tasks[self.cta_task_begin[b]:self.cta_task_begin[b + 1]]
@@ -140,9 +141,10 @@ def build_plan(n_quads, grid, cap_quads, overhead_quads=DEFAULT_OVERHEAD_QUADS, 
     if np.any(n_quads < 1):
         raise ValueError('every chain needs at least one datum')
     grid = int(grid)
-    cmin = np.maximum(1, -(-n_quads // int(cap_quads))).astype(np.int64)
+    cap_quads = np.broadcast_to(np.asarray(cap_quads, dtype=np.int64), n_quads.shape)   # per chain
+    cmin = np.maximum(1, -(-n_quads // cap_quads)).astype(np.int64)
     if cmin.max() > grid:
-        raise ValueError(f'a chain needs {int(cmin.max())} CTAs of {cap_quads} quads; grid has {grid}')
+        raise ValueError(f'a chain needs {int(cmin.max())} CTAs; the grid has {grid}')
 
     order = np.argsort(-cost_q, kind='stable')
     qs, cs = cost_q[order], cmin[order]

@@ -132,6 +132,8 @@ typedef struct brta_batch {
                                       (labels stay in canonical order)                          */
     const int64_t*  perm_offset;   /* [R] element offsets into perm                        */
     const int32_t*  n_data;        /* [R] N_r                                            */
+    const uint32_t* max_tick;      /* [R] largest tick of the chain: below 65536 the chain's slices sit
+                                      in shared memory at 8 B per quad, else 16 B                  */
     const uint32_t* chain_id;      /* [R] Philox counter word identifying the chain      */
     const float*    ts;            /* [R] time step (gibbs.py:147-151)                   */
     const float*    whyper;        /* [R,K] Dirichlet prior (gibbs.py:173)               */
@@ -162,7 +164,8 @@ typedef struct brta_batch {
     const brta_task* tasks;        /* tasks of CTA b: tasks[cta_task_begin[b] .. cta_task_begin[b+1]) */
     const int32_t*   cta_task_begin; /* [grid_ctas + 1]                                  */
     int32_t          grid_ctas;    /* must equal sm_count * ctas_per_sm or less          */
-    int32_t          slice_cap_quads; /* largest quad_count over all tasks               */
+    int32_t          slice_cap_quads; /* dynamic shared memory per CTA in 16-byte units: the largest
+                                         task slice (a quad takes 16 B, or 8 B if max_tick < 65536)   */
     /* one chain sharded over several GPUs (config C4): n_shards > 1 requires n_chains == 1.  Each GPU
      * sweeps a contiguous range of the chain's quads (tasks carry GLOBAL quad indices; tick_offset /
      * ind_offset are shifted by the caller so that global indices address the local shard) and the GPUs
