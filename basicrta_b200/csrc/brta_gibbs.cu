@@ -285,25 +285,31 @@ __device__ __forceinline__ void build_table_row(float tick, const float2* __rest
         *reinterpret_cast<float4*>(row + k) = make_float4(l[k], l[k + 1], l[k + 2], l[k + 3]);
 }
 
-// label of one datum from its memoised row; returns true if the row underflowed (FAST only)
+// label of one datum from its memoised row; returns true if the row underflowed (FAST only).
+// The inverse-CDF search runs directly on the row in shared memory: log2(KP) dependent 4-byte
+// loads instead of fetching the whole row and searching it in registers.  Entries past K hold the
+// total, which never compares <= thr (thr < total), so they act as +inf padding; within a warp the
+// data are neighbours in tick order, hence mostly the same row and a handful of distinct addresses.
 template <int K>
 __device__ __forceinline__ bool label_from_table(uint32_t tick, float f12, const TableView& tab, int kmax, int& lab)
 {
     constexpr int KP = table_row_floats(K);
-    const uint32_t r = tick - tab.lo;
-    const float4* const rp = reinterpret_cast<const float4*>(tab.rows + (size_t)r * KP);
-    float cum[K];
-#pragma unroll
-    for (int k4 = 0; k4 < KP / 4; ++k4) {
-        const float4 v = rp[k4];
-        if (4 * k4 + 0 < K) cum[4 * k4 + 0] = v.x;
-        if (4 * k4 + 1 < K) cum[4 * k4 + 1] = v.y;
-        if (4 * k4 + 2 < K) cum[4 * k4 + 2] = v.z;
-        if (4 * k4 + 3 < K) cum[4 * k4 + 3] = v.w;
-    }
-    const float total = cum[K - 1];
+    constexpr int TOP = (KP > 16) ? 32 : (KP > 8) ? 16 : (KP > 4) ? 8 : 4;      // power of two >= KP
+    const float* const row = tab.rows + (size_t)(tick - tab.lo) * KP;
+    const float total = row[KP - 1];
     const float thr = __fmaf_rn(f12, total, -total);
-    lab = min(count_le<K>(cum, thr), kmax);
+    int pos = 0;                                           // number of entries <= thr found so far
+#pragma unroll
+    for (int step = TOP / 2; step >= 1; step >>= 1) {
+        const int probe = pos + step - 1;
+        if (TOP > KP) {                                    // rows are KP long: probes past the end count as +inf
+            if (probe < KP && row[probe] <= thr) pos += step;
+        } else {
+            if (row[probe] <= thr) pos += step;
+        }
+    }
+    // pos counts entries of the first TOP - 1; the last one (index TOP - 1 >= K - 1 ... ) is the total or padding
+    lab = min(pos, kmax);
     return !(total > 8.0779357e-28f);
 }
 
