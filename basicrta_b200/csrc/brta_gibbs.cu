@@ -244,6 +244,9 @@ __device__ __forceinline__ void red_shared_stats(uint32_t cnt_addr, uint32_t tic
 // FFMA + MUFU + FADD per datum.  Quads beyond the table (the sparse tail) take the direct path.
 constexpr int TABLE_FLOATS = 4096;                          // 16 KB of shared memory per CTA
 __host__ __device__ constexpr int table_row_floats(int k) { return (k + 3) / 4 * 4; }
+// rows are laid out with an odd stride so that the same entry of neighbouring rows (what the lanes
+// of a warp read during the search) falls into different banks
+__host__ __device__ constexpr int table_row_stride(int k) { return table_row_floats(k) + 1; }
 
 struct TableView {
     const float* rows;       // shared memory, row r = cumulative sums of tick lo + r
@@ -281,8 +284,7 @@ __device__ __forceinline__ void build_table_row(float tick, const float2* __rest
 #pragma unroll
     for (int k = K; k < KP; ++k) l[k] = cum;
 #pragma unroll
-    for (int k = 0; k < KP; k += 4)
-        *reinterpret_cast<float4*>(row + k) = make_float4(l[k], l[k + 1], l[k + 2], l[k + 3]);
+    for (int k = 0; k < KP; ++k) row[k] = l[k];
 }
 
 // label of one datum from its memoised row; returns true if the row underflowed (FAST only).
@@ -295,7 +297,7 @@ __device__ __forceinline__ bool label_from_table(uint32_t tick, float f12, const
 {
     constexpr int KP = table_row_floats(K);
     constexpr int TOP = (KP > 16) ? 32 : (KP > 8) ? 16 : (KP > 4) ? 8 : 4;      // power of two >= KP
-    const float* const row = tab.rows + (size_t)(tick - tab.lo) * KP;
+    const float* const row = tab.rows + (size_t)(tick - tab.lo) * table_row_stride(K);
     const float total = row[KP - 1];
     const float thr = __fmaf_rn(f12, total, -total);
     int pos = 0;                                           // number of entries <= thr found so far
@@ -562,13 +564,12 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
             rh_b = b.rhyper[((size_t)r * kreal + lane) * 2 + 1];
         }
         // memoised rows cover ticks lo .. lo + table_rows - 1 of this slice
-        constexpr int KP = table_row_floats(K);
         unsigned tick_lo = 0xffffffffu, tick_hi = 0u;
 #pragma unroll
         for (int w = 0; w < WARPS; ++w) { tick_lo = min(tick_lo, s_red_lo[w]); tick_hi = max(tick_hi, s_red_hi[w]); }
         int table_rows = 0;
         if (!(b.flags & BRTA_FLAG_NO_TABLE) && tick_lo <= tick_hi)
-            table_rows = (int)min((unsigned)(TABLE_FLOATS / KP), tick_hi - tick_lo + 1u);
+            table_rows = (int)min((unsigned)(TABLE_FLOATS / table_row_stride(K)), tick_hi - tick_lo + 1u);
         TableView tab;
         tab.rows = s_table;
         tab.lo = tick_lo;
@@ -595,7 +596,8 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
             }
             if (table_rows > 0) {                          // cumulative rows of this iteration's coefficients
                 for (int rr = tid; rr < table_rows; rr += THREADS)
-                    build_table_row<K, EXACT>((float)(tick_lo + (unsigned)rr), s_coef, s_table + (size_t)rr * KP);
+                    build_table_row<K, EXACT>((float)(tick_lo + (unsigned)rr), s_coef,
+                                              s_table + (size_t)rr * table_row_stride(K));
                 __syncthreads();
             }
             const bool save = (j % thin == 0);

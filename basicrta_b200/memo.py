@@ -16,7 +16,8 @@ COST_DIRECT = 1.0                        # quad-times of a recomputed quad
 
 
 def table_rows(ncomp):
-    return TABLE_FLOATS // ((int(ncomp) + 3) // 4 * 4)
+    """Rows of the kernel's table: TABLE_FLOATS / table_row_stride(K) (odd stride, see brta_gibbs.cu)."""
+    return TABLE_FLOATS // ((int(ncomp) + 3) // 4 * 4 + 1)
 
 
 class ChainCost:
