@@ -207,7 +207,7 @@ __device__ __forceinline__ unsigned draw_labels(const float (&tick)[D], const fl
         for (int d = 0; d < D; ++d) {
             const float thr = __fmaf_rn(f12[d], cum[d], -cum[d]);
             lab[d] = min(count_le<K>(l[d], thr), kmax);
-            if (!(cum[d] > 8.0779357e-28f)) redo |= 1u << d;   // total < 2^-90 (or NaN)
+            if (!(cum[d] > 8.0779357e-28f)) redo |= 1u << d;   // total < 2^-90 (or NaN): TOTAL_FLOOR
         }
     }
     return redo;
@@ -249,10 +249,51 @@ __host__ __device__ constexpr int table_row_floats(int k) { return (k + 3) / 4 *
 __host__ __device__ constexpr int table_row_stride(int k) { return table_row_floats(k) + 1; }
 
 struct TableView {
-    const float* rows;       // shared memory, row r = cumulative sums of tick lo + r
+    uint32_t addr;           // shared-window byte address of row 0; row r = cumulative sums of tick lo + r
     uint32_t lo;             // first tick of the table
     uint32_t limit;          // quads with every tick < limit are served from the table (0: no table)
 };
+
+// Shared-memory accesses of the hot loop by explicit 32-bit address.  The compiler otherwise
+// re-derives the shared-window base of every access from SR_CgaCtaId (an S2UR + uniform-datapath
+// chain ahead of each load / reduction: a sixth of the stall samples of the first memoised kernel);
+// the kernels read the base once, through opaque_u32, and keep it in a register.
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t x)
+{
+    uint32_t y;
+    asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+template <int OFF>
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+// ticks of quad q of a staged slice: 8 B per quad (16-bit ticks) or 16 B
+template <bool T16>
+__device__ __forceinline__ uint4 lds_quad(uint32_t slice_addr, int q)
+{
+    if constexpr (T16) {
+        const uint2 raw = lds_v2(slice_addr + 8u * (uint32_t)q);
+        return make_uint4(raw.x & 0xffffu, raw.x >> 16, raw.y & 0xffffu, raw.y >> 16);
+    } else {
+        return lds_v4(slice_addr + 16u * (uint32_t)q);
+    }
+}
 
 template <int K, bool EXACT>
 __device__ __forceinline__ void build_table_row(float tick, const float2* __restrict__ s_coef, float* __restrict__ row)
@@ -292,27 +333,38 @@ __device__ __forceinline__ void build_table_row(float tick, const float2* __rest
 // loads instead of fetching the whole row and searching it in registers.  Entries past K hold the
 // total, which never compares <= thr (thr < total), so they act as +inf padding; within a warp the
 // data are neighbours in tick order, hence mostly the same row and a handful of distinct addresses.
+// Returns 4 * (number of row entries <= u * total), i.e. the label as a byte offset into the
+// statistics array, and the row total.
 template <int K>
-__device__ __forceinline__ bool label_from_table(uint32_t tick, float f12, const TableView& tab, int kmax, int& lab)
+__device__ __forceinline__ uint32_t search_row(uint32_t tick, float f12, const TableView& tab, float& total)
 {
     constexpr int KP = table_row_floats(K);
     constexpr int TOP = (KP > 16) ? 32 : (KP > 8) ? 16 : (KP > 4) ? 8 : 4;      // power of two >= KP
-    const float* const row = tab.rows + (size_t)(tick - tab.lo) * table_row_stride(K);
-    const float total = row[KP - 1];
+    const uint32_t row = tab.addr + (tick - tab.lo) * (uint32_t)(4 * table_row_stride(K));
+    total = lds_f32<4 * (KP - 1)>(row);
     const float thr = __fmaf_rn(f12, total, -total);
-    int pos = 0;                                           // number of entries <= thr found so far
-#pragma unroll
-    for (int step = TOP / 2; step >= 1; step >>= 1) {
-        const int probe = pos + step - 1;
-        if (TOP > KP) {                                    // rows are KP long: probes past the end count as +inf
-            if (probe < KP && row[probe] <= thr) pos += step;
-        } else {
-            if (row[probe] <= thr) pos += step;
-        }
+    uint32_t p = row;                                      // row + 4 * (number of entries <= thr found so far)
+#define BRTA_PROBE(STEP)                                                                          \
+    if constexpr (TOP / 2 >= STEP) {                                                                  \
+        const float v = lds_f32<4 * (STEP - 1)>(p);                                                   \
+        /* rows are KP long: probes past the end count as +inf */                                     \
+        const bool in_row = (TOP == KP) || (p + 4u * (STEP - 1) < row + 4u * KP);                     \
+        if (in_row && v <= thr) p += 4u * STEP;                                                       \
     }
-    // pos counts entries of the first TOP - 1; the last one (index TOP - 1 >= K - 1 ... ) is the total or padding
-    lab = min(pos, kmax);
-    return !(total > 8.0779357e-28f);
+    BRTA_PROBE(16) BRTA_PROBE(8) BRTA_PROBE(4) BRTA_PROBE(2) BRTA_PROBE(1)
+#undef BRTA_PROBE
+    return p - row;
+}
+
+// FAST mode: a total below 2^-90 (every term underflowed) sends the datum to draw_label_safe
+constexpr float TOTAL_FLOOR = 8.0779357e-28f;
+
+template <int K>
+__device__ __forceinline__ bool label_from_table(uint32_t tick, float f12, const TableView& tab, int kmax, int& lab)
+{
+    float total;
+    lab = min((int)(search_row<K>(tick, f12, tab, total) >> 2), kmax);
+    return !(total > TOTAL_FLOOR);
 }
 
 // One quad (4 data) of the sweep: labels, statistics, optional label store.
@@ -378,24 +430,96 @@ __device__ __forceinline__ void sweep_quad(const uint4 tk, const float4 f12, con
     }
 }
 
-template <int K, bool EXACT, bool SAVE>
-__device__ __forceinline__ void sweep_slice(const unsigned char* __restrict__ s_ticks, bool ticks16,
-                                            const float2* __restrict__ s_coef,
-                                            int nq, int qb, int n_data, int kmax, int dom, uint32_t j,
-                                            uint32_t chain_id, const RoundKeys& rk,
-                                            const float4* __restrict__ u_row, uint32_t stat_addr,
-                                            uint8_t* ind_row, const int32_t* __restrict__ perm, const TableView& tab)
+// U quads of the served prefix at once: U Philox blocks and 4U row searches in flight per thread.
+// The chain of dependent shared-memory loads of one search is what the warp waits for; with
+// only four CTAs of four warps per SM the extra independent work is what fills those slots.
+#ifndef BRTA_SERVED_UNROLL
+#define BRTA_SERVED_UNROLL 2
+#endif
+template <int K, bool SAVE, bool T16, int U>
+__device__ __forceinline__ void sweep_served(uint32_t slice_addr, int q0, int qb, int kmax, int dom, uint32_t j,
+                                             uint32_t chain_id, const RoundKeys& rk, uint32_t stat_addr,
+                                             uint8_t* ind_row, const int32_t* __restrict__ perm, const TableView& tab,
+                                             const float2* __restrict__ s_coef)
 {
+    uint32_t tis[U][4];
+    float fs[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int q = q0 + u * THREADS;
+        const uint4 tk = lds_quad<T16>(slice_addr, q);
+        tis[u][0] = tk.x; tis[u][1] = tk.y; tis[u][2] = tk.z; tis[u][3] = tk.w;
+        const Words4 w = philox4x32_10_rk((uint32_t)(qb + q), j, chain_id, 0u, rk);
+        fs[u][0] = word_to_12(w.x); fs[u][1] = word_to_12(w.y); fs[u][2] = word_to_12(w.z); fs[u][3] = word_to_12(w.w);
+    }
+    // label as byte offset 4 * k.  With a usable row (0 < total < inf) the last real entry equals the
+    // total and u * total < total, so the count never passes K - 1 and needs no clamp.
+    uint32_t off[U][4];
+    float lowest = INFINITY;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            float total;
+            off[u][d] = search_row<K>(tis[u][d], fs[u][d], tab, total);
+            lowest = fminf(lowest, total);
+        }
+    if (!(lowest > TOTAL_FLOOR)) {                         // cold: a row underflowed (FAST mode only)
+        constexpr int KP = table_row_floats(K);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const float total = lds_f32<4 * (KP - 1)>(tab.addr + (tis[u][d] - tab.lo) * (uint32_t)(4 * table_row_stride(K)));
+                if (!(total > TOTAL_FLOOR))
+                    off[u][d] = 4u * (uint32_t)draw_label_safe<K>(tick_to_float(tis[u][d]), fs[u][d], s_coef, kmax);
+            }
+    }
+    const uint32_t dom_off = 4u * (uint32_t)dom;
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+            if (off[u][d] != dom_off) red_shared_stats(stat_addr + off[u][d], tis[u][d]);
+    if (SAVE) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i0 = (qb + q0 + u * THREADS) * 4;        // served quads are full quads
+#pragma unroll
+            for (int d = 0; d < 4; ++d) ind_row[perm ? perm[i0 + d] : i0 + d] = (uint8_t)(off[u][d] >> 2);
+        }
+    }
+}
+
+// One iteration's sweep over a staged slice (`slice_addr`: its shared-window address).
+// `n_served`: the first n_served quads are full quads with every tick inside the memoised rows
+// (with the chain in ascending-tick order: all the served quads); they run U at a time without
+// any per-quad case distinction, the rest through sweep_quad.
+template <int K, bool EXACT, bool SAVE, bool T16>
+__device__ __forceinline__ void sweep_slice_t(uint32_t slice_addr, const float2* __restrict__ s_coef,
+                                              int nq, int qb, int n_data, int kmax, int dom, uint32_t j,
+                                              uint32_t chain_id, const RoundKeys& rk,
+                                              const float4* __restrict__ u_row, uint32_t stat_addr,
+                                              uint8_t* ind_row, const int32_t* __restrict__ perm, const TableView& tab,
+                                              int n_served)
+{
+    constexpr int U = BRTA_SERVED_UNROLL;
+    int q_done = 0;
+    if (u_row == nullptr) {                                // injected uniforms (tests) take the general loop
+        q_done = n_served / (U * THREADS) * (U * THREADS);
+        for (int q = threadIdx.x; q < q_done; q += U * THREADS)
+            sweep_served<K, SAVE, T16, U>(slice_addr, q, qb, kmax, dom, j, chain_id, rk, stat_addr, ind_row, perm, tab, s_coef);
+        if constexpr (U > 1) {
+            const int q_one = n_served / THREADS * THREADS;
+            for (int q = q_done + threadIdx.x; q < q_one; q += THREADS)
+                sweep_served<K, SAVE, T16, 1>(slice_addr, q, qb, kmax, dom, j, chain_id, rk, stat_addr, ind_row, perm, tab, s_coef);
+            q_done = q_one;
+        }
+    }
     // at most one quad of the whole chain is partial; find out once whether it is in this slice
     const int tail_q = ((n_data & 3) != 0) ? (n_data >> 2) - qb : -1;
-    for (int q = threadIdx.x; q < nq; q += THREADS) {
-        uint4 tk;                                          // shared memory holds the ticks as stored: 8 or 16 B per quad
-        if (ticks16) {
-            const uint2 raw = reinterpret_cast<const uint2*>(s_ticks)[q];
-            tk = make_uint4(raw.x & 0xffffu, raw.x >> 16, raw.y & 0xffffu, raw.y >> 16);
-        } else {
-            tk = reinterpret_cast<const uint4*>(s_ticks)[q];
-        }
+    for (int q = q_done + threadIdx.x; q < nq; q += THREADS) {
+        const uint4 tk = lds_quad<T16>(slice_addr, q);
         float4 f12;
         if (u_row != nullptr) {
             const float4 uu = u_row[qb + q];
@@ -407,6 +531,50 @@ __device__ __forceinline__ void sweep_slice(const unsigned char* __restrict__ s_
         sweep_quad<K, EXACT, SAVE>(tk, f12, s_coef, kmax, dom, (qb + q) * 4, n_data, q == tail_q,
                                    stat_addr, ind_row, perm, tab);
     }
+}
+
+template <int K, bool EXACT, bool SAVE>
+__device__ __forceinline__ void sweep_slice(uint32_t slice_addr, bool ticks16, const float2* __restrict__ s_coef,
+                                            int nq, int qb, int n_data, int kmax, int dom, uint32_t j,
+                                            uint32_t chain_id, const RoundKeys& rk,
+                                            const float4* __restrict__ u_row, uint32_t stat_addr,
+                                            uint8_t* ind_row, const int32_t* __restrict__ perm, const TableView& tab,
+                                            int n_served)
+{
+    if (ticks16)
+        sweep_slice_t<K, EXACT, SAVE, true>(slice_addr, s_coef, nq, qb, n_data, kmax, dom, j, chain_id, rk, u_row,
+                                            stat_addr, ind_row, perm, tab, n_served);
+    else
+        sweep_slice_t<K, EXACT, SAVE, false>(slice_addr, s_coef, nq, qb, n_data, kmax, dom, j, chain_id, rk, u_row,
+                                             stat_addr, ind_row, perm, tab, n_served);
+}
+
+// length of the served prefix of a staged slice: the first quad that is partial or has a tick
+// outside [lo, limit) ends it.  Block-wide; `s_scratch` holds WARPS words.
+__device__ __forceinline__ int served_prefix(const unsigned char* __restrict__ s_ticks, bool ticks16, int nq, int qb,
+                                             int n_data, unsigned limit, unsigned* s_scratch)
+{
+    unsigned first = (unsigned)nq;
+    for (int q = threadIdx.x; q < nq; q += THREADS) {
+        unsigned hi;
+        if (ticks16) {
+            const uint2 raw = reinterpret_cast<const uint2*>(s_ticks)[q];
+            hi = max(max(raw.x & 0xffffu, raw.x >> 16), max(raw.y & 0xffffu, raw.y >> 16));
+        } else {
+            const uint4 raw = reinterpret_cast<const uint4*>(s_ticks)[q];
+            hi = max(max(raw.x, raw.y), max(raw.z, raw.w));
+        }
+        if ((qb + q) * 4 + 3 >= n_data || hi >= limit) { first = (unsigned)q; break; }
+    }
+    first = __reduce_min_sync(FULL, first);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_scratch[threadIdx.x >> 5] = first;
+    __syncthreads();
+    unsigned r = s_scratch[0];
+#pragma unroll
+    for (int w = 1; w < WARPS; ++w) r = min(r, s_scratch[w]);
+    __syncthreads();
+    return (int)r;
 }
 
 // Developer-only phase timing (-DBRTA_PHASE_TIMING builds a debug library): thread 0 of
@@ -456,8 +624,10 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
     __shared__ __align__(16) unsigned s_stat[64];
     unsigned* const s_cnt = s_stat;
     unsigned* const s_sum = s_stat + 32;
-    uint32_t stat_addr = (uint32_t)__cvta_generic_to_shared(s_stat);
-    __shared__ __align__(16) float s_table[TABLE_FLOATS];  // memoised cumulative rows of the running iteration
+    __shared__ __align__(16) float s_table[TABLE_FLOATS + 32];  // memoised cumulative rows of the running iteration (+ probe overrun)
+    const uint32_t stat_addr = opaque_u32((uint32_t)__cvta_generic_to_shared(s_stat));
+    const uint32_t slice_addr = opaque_u32((uint32_t)__cvta_generic_to_shared(smem_raw));
+    const uint32_t table_addr = opaque_u32((uint32_t)__cvta_generic_to_shared(s_table));
     __shared__ unsigned s_red_lo[WARPS], s_red_hi[WARPS];  // smallest / largest tick of the slice
     __shared__ unsigned long long s_red_t[WARPS];
     __shared__ unsigned s_red_n[WARPS];
@@ -571,9 +741,10 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
         if (!(b.flags & BRTA_FLAG_NO_TABLE) && tick_lo <= tick_hi)
             table_rows = (int)min((unsigned)(TABLE_FLOATS / table_row_stride(K)), tick_hi - tick_lo + 1u);
         TableView tab;
-        tab.rows = s_table;
+        tab.addr = table_addr;
         tab.lo = tick_lo;
         tab.limit = table_rows > 0 ? tick_lo + (unsigned)table_rows : 0u;
+        const int n_served = served_prefix(smem_raw, ticks16, nq, qb, n_data, tab.limit, s_red_lo);
         unsigned char* const exch = static_cast<unsigned char*>(b.exchange) + b.exch_offset[r];
         // mailbox layout: slot[parity][member][32] of {tag<<32 | n_k, tag<<32 | tick sum}
         ulonglong2* const mbox = reinterpret_cast<ulonglong2*>(exch);
@@ -609,11 +780,11 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
 
             // ---- indicator draws + sufficient statistics (gibbs.py:196-207) -------------
             if (save)
-                sweep_slice<K, EXACT, true>(smem_raw, ticks16, s_coef, nq, qb, n_data, kreal - 1, dom, (uint32_t)j, chain_id,
-                                            prm.rk, u_row, stat_addr, ind_base + (size_t)row * ind_stride, perm, tab);
+                sweep_slice<K, EXACT, true>(slice_addr, ticks16, s_coef, nq, qb, n_data, kreal - 1, dom, (uint32_t)j, chain_id,
+                                            prm.rk, u_row, stat_addr, ind_base + (size_t)row * ind_stride, perm, tab, n_served);
             else
-                sweep_slice<K, EXACT, false>(smem_raw, ticks16, s_coef, nq, qb, n_data, kreal - 1, dom, (uint32_t)j, chain_id,
-                                             prm.rk, u_row, stat_addr, nullptr, nullptr, tab);
+                sweep_slice<K, EXACT, false>(slice_addr, ticks16, s_coef, nq, qb, n_data, kreal - 1, dom, (uint32_t)j, chain_id,
+                                             prm.rk, u_row, stat_addr, nullptr, nullptr, tab, n_served);
             PHASE_MARK(0);                                 // sweep
             __syncthreads();
             PHASE_MARK(1);                                 // wait for the CTA's slowest warp
@@ -899,7 +1070,11 @@ int cuda_fail(cudaError_t e, const char* where)
 
 typedef void (*kernel_fn)(const SweepParams);
 
-struct Variant { int k; kernel_fn fast; kernel_fn exact; };
+struct Variant {
+    int k;
+    kernel_fn fast, exact;
+    kernel_fn pick(uint32_t flags) const { return (flags & BRTA_FLAG_EXACT) ? exact : fast; }
+};
 
 #define BRTA_VARIANT(KK) {KK, gibbs_sweep_kernel<KK, false>, gibbs_sweep_kernel<KK, true>}
 const Variant g_variants[] = {
@@ -950,7 +1125,7 @@ int brta_gibbs_launch_info(int device, int ncomp, uint32_t flags, int slice_cap_
     if (!info) return brta::fail(BRTA_E_NULL, "brta_gibbs_launch_info: info is NULL");
     const brta::Variant* v = brta::pick_variant(ncomp);
     if (ncomp < 1 || !v) return brta::fail(BRTA_E_NCOMP, "ncomp must be in 1..32");
-    brta::kernel_fn fn = (flags & BRTA_FLAG_EXACT) ? v->exact : v->fast;
+    brta::kernel_fn fn = v->pick(flags);
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return brta::cuda_fail(e, "cudaSetDevice");
     const size_t smem = (size_t)slice_cap_quads * 16;
@@ -1000,7 +1175,7 @@ int brta_gibbs_run_batch(const brta_batch* batch, void* stream)
     if ((b.flags & BRTA_FLAG_TRACE) && (!b.trace_nk || !b.trace_tk))
         return brta::fail(BRTA_E_NULL, "TRACE needs trace_nk and trace_tk");
 
-    brta::kernel_fn fn = (b.flags & BRTA_FLAG_EXACT) ? v->exact : v->fast;
+    brta::kernel_fn fn = v->pick(b.flags);
     const size_t smem = (size_t)b.slice_cap_quads * 16;
     cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return brta::cuda_fail(e, "cudaFuncSetAttribute(smem)");

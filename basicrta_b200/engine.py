@@ -177,6 +177,7 @@ class GibbsEngine:
         if niter < 1 or thin < 1:
             raise ValueError('niter and thin must be >= 1')
         rows = (niter + 1) // thin
+        flags = int(flags)
         n_data = np.array([len(c.ticks) for c in chains], dtype=np.int64)
         if R == 0 or n_data.min() < 1:
             raise ValueError('every chain needs at least one datum')

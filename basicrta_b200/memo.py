@@ -11,7 +11,7 @@ other every iteration, hence slices must take equal time, not hold equal counts.
 import numpy as np
 
 TABLE_FLOATS = 4096                      # must match TABLE_FLOATS in csrc/brta_gibbs.cu
-COST_SERVED = 0.62                       # quad-times of a quad read from the table (~240 of ~400 instructions)
+COST_SERVED = 0.5                        # quad-times of a quad read from the table (measured optimum on B200)
 COST_DIRECT = 1.0                        # quad-times of a recomputed quad
 
 

@@ -27,9 +27,14 @@ if nd:
 else:
     ticks = bench.workload(range(n_chains))
 chains = [ChainInput(ticks=t, ts=0.1, chain_id=i) for i, t in enumerate(ticks)]
+cs = os.environ.get('BRTA_COST_SERVED')
+if cs:
+    from basicrta_b200 import memo
+    memo.COST_SERVED = float(cs)
 cps = os.environ.get('BRTA_CTAS_PER_SM')
 nw = os.environ.get('BRTA_WAVES')
-eng = GibbsEngine(0, ctas_per_sm=int(cps) if cps else None)
+ov = os.environ.get('BRTA_OVERHEAD')
+eng = GibbsEngine(0, ctas_per_sm=int(cps) if cps else None, overhead_quads=float(ov) if ov else None)
 db = eng.prepare(chains, 15, niter, thin=100, seed=1, n_waves=int(nw) if nw else None,
                  flags=_cabi.FLAG_NO_TABLE if 'notable' in sys.argv else 0)
 p = db.plan
