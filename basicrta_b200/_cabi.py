@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get('BRTA_LIB', os.path.join(HERE, 'libbrta_gibbs.so'))   
 SRC = os.path.join(HERE, 'csrc', 'brta_gibbs.cu')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 THREADS = 128
 MAX_NCOMP = 32
 TICK_LIMIT = 1 << 23
@@ -79,6 +79,7 @@ class Batch(C.Structure):
         ('n_shards', C.c_int32), ('shard_rank', C.c_int32), ('shard_mailbox', C.c_void_p),
         ('shard_totals', C.c_void_p),
         ('exchange', C.c_void_p), ('exch_offset', C.c_void_p),
+        ('task_cycles', C.c_void_p),
     ]
 
 

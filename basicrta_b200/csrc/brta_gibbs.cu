@@ -754,8 +754,10 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
         unsigned* const ex_arrive = reinterpret_cast<unsigned*>(exch + EXCH_ARRIVE_OFF);
 
         bool bad = false;
+        unsigned long long busy_cycles = 0;                // schedule feedback: iteration start -> post
         PHASE_DECL
         for (int j = 1; j <= niter; ++j) {
+            const long long iter_t0 = b.task_cycles ? clock64() : 0;
             if (inject_coef) {
                 if (tid < kreal) {
                     const size_t o = ((size_t)r * niter + (j - 1)) * kreal + tid;
@@ -788,6 +790,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
             PHASE_MARK(0);                                 // sweep
             __syncthreads();
             PHASE_MARK(1);                                 // wait for the CTA's slowest warp
+            if (b.task_cycles && 2 * j > niter) busy_cycles += (unsigned long long)(clock64() - iter_t0);
 
             // ---- this CTA's partials; the uncounted dominant label follows by subtraction --
             if (warp == 0) {
@@ -1019,6 +1022,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
             PHASE_MARK(7);
         }
         PHASE_FLUSH;
+        if (b.task_cycles && tid == 0) b.task_cycles[ti] = busy_cycles;
         if (bad) atomicOr(&s_bad, 1u);
         __syncthreads();
         if (tid == 0 && s_bad) atomicOr(reinterpret_cast<unsigned*>(&b.status[r]), (unsigned)BRTA_STATUS_NONFINITE);

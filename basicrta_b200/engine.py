@@ -26,8 +26,8 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import _cabi
-from .memo import ChainCost
-from .plan import build_plan
+from .memo import COST_DIRECT, COST_SERVED, ChainCost
+from .plan import build_plan, rebalance_team
 
 LOG2E = 1.4426950408889634
 
@@ -113,6 +113,11 @@ class DeviceBatch:
     executed_ex2_share: float = 1.0                   # ex2 actually executed / units (memoised rows make it < 1)
 
 
+CALIBRATE_MIN_NITER = 2000     # shorter runs are not worth the calibration launches
+CALIBRATE_ITERS = 96           # iterations per calibration launch (the kernel times the second half)
+CALIBRATE_ROUNDS = 2
+
+
 class GibbsEngine:
     """One engine per GPU.  ``prepare`` (pack + H2D), ``launch`` (async kernel),
     ``fetch`` (D2H) are separate so callers can time and overlap them."""
@@ -157,13 +162,15 @@ class GibbsEngine:
         # dynamic shared memory in 16-byte units: the largest task slice
         units = np.where(narrow[plan.tasks['chain']], (plan.tasks['quad_count'] + 1) // 2, plan.tasks['quad_count'])
         plan.smem_units = int(units.max())
+        plan.cap_quads, plan.cap_units = cap, int(cap16)
         check = _cabi.launch_info(self.device, ncomp, flags, plan.smem_units)
         if check.ctas_per_sm < per_sm:
             raise _cabi.BrtaError('schedule assumes more co-resident CTAs than the device grants')
         return plan
 
     # ---- pack + upload -------------------------------------------------------------------
-    def prepare(self, chains, ncomp, niter, thin=100, seed=0, flags=0, inject=None, n_waves=None, shard=None):
+    def prepare(self, chains, ncomp, niter, thin=100, seed=0, flags=0, inject=None, n_waves=None, shard=None,
+                calibrate=None):
         """``chains``: list of :class:`ChainInput`.  ``inject``: dict with optional
         ``coef_c``/``coef_a`` (list of [niter,K] float32) and ``u`` (list of [niter,N]).
         ``shard`` (internal, see :func:`run_sharded`): this GPU's part of ONE chain split over
@@ -178,6 +185,7 @@ class GibbsEngine:
             raise ValueError('niter and thin must be >= 1')
         rows = (niter + 1) // thin
         flags = int(flags)
+        costs = None
         n_data = np.array([len(c.ticks) for c in chains], dtype=np.int64)
         if R == 0 or n_data.min() < 1:
             raise ValueError('every chain needs at least one datum')
@@ -322,24 +330,102 @@ class GibbsEngine:
             b.trace_tk = dev_zeros('trace_tk', (R, niter, K), torch.int64)
 
         torch.cuda.current_stream(dev).synchronize()
-        ex2_share = 1.0
+        db = DeviceBatch(batch=b, plan=plan, tensors=T, host=H, order=order, n_data=n_data, ind_offset=ind_offset,
+                         rows=rows, ncomp=K, niter=int(niter), flags=int(flags), h2d_bytes=h2d,
+                         units=float(n_data.sum()) * K * int(niter))
+        if calibrate is None:
+            calibrate = (shard is None and niter >= CALIBRATE_MIN_NITER and int(plan.team_size.max()) > 1 and
+                         not flags & (_cabi.FLAG_INJECT_COEF | _cabi.FLAG_INJECT_U | _cabi.FLAG_TRACE))
+        if calibrate:
+            if shard is not None or flags & (_cabi.FLAG_INJECT_COEF | _cabi.FLAG_INJECT_U | _cabi.FLAG_TRACE):
+                raise ValueError('calibration needs a plain (not sharded, not injected, not traced) batch')
+            for _ in range(CALIBRATE_ROUNDS):
+                self._calibrate(db, costs, ticks, tick_offset)
         if shard is None and costs is not None:
-            done = 0.0
-            for task in plan.tasks:
-                cc = costs[int(task['chain'])]
-                s0, e0 = int(task['quad_begin']), int(task['quad_begin'] + task['quad_count'])
-                k = cc.served(s0, e0)
-                rows_built = 0
-                if k > 0:
-                    hi_tick = int(cc.qmax[min(e0, cc.n_full) - 1]) if min(e0, cc.n_full) > s0 else int(cc.qmin[s0])
-                    rows_built = min(cc.rows, hi_tick - int(cc.qmin[s0]) + 1)
-                done += 4.0 * (e0 - s0 - k) + rows_built
-            ex2_share = done / float(n_data.sum())
+            db.executed_ex2_share = self._executed_ex2_share(plan, costs, float(n_data.sum()))
         if shard is not None:
-            n_data, ind_offset = n_local, ind_offset + d0            # host-side views are shard-local
-        return DeviceBatch(batch=b, plan=plan, tensors=T, host=H, order=order, n_data=n_data, ind_offset=ind_offset,
-                           rows=rows, ncomp=K, niter=int(niter), flags=int(flags), h2d_bytes=h2d,
-                           units=float(n_data.sum()) * K * int(niter), executed_ex2_share=ex2_share)
+            db.n_data, db.ind_offset = n_local, ind_offset + d0      # host-side views are shard-local
+        return db
+
+    @staticmethod
+    def _executed_ex2_share(plan, costs, n_total):
+        """ex2 actually issued per algorithmic unit: recomputed data + memoised rows built."""
+        done = 0.0
+        for task in plan.tasks:
+            cc = costs[int(task['chain'])]
+            s0, e0 = int(task['quad_begin']), int(task['quad_begin'] + task['quad_count'])
+            k = cc.served(s0, e0)
+            rows_built = 0
+            if k > 0:
+                hi_tick = int(cc.qmax[min(e0, cc.n_full) - 1]) if min(e0, cc.n_full) > s0 else int(cc.qmin[s0])
+                rows_built = min(cc.rows, hi_tick - int(cc.qmin[s0]) + 1)
+            done += 4.0 * (e0 - s0 - k) + rows_built
+        return done / n_total
+
+    def _measure(self, db, iters):
+        """Cycles per task from the start of an iteration to the post of its partials (a short launch
+        with ``task_cycles`` set; outputs untouched, workspace reset afterwards)."""
+        torch = self.torch
+        T = db.tensors
+        cyc = torch.zeros(len(db.plan.tasks), dtype=torch.int64, device=T['tasks'].device)
+        cal = _cabi.Batch.from_buffer_copy(db.batch)
+        cal.niter, cal.thin = int(iters), int(iters) + 2            # no row is saved
+        cal.task_cycles = cyc.data_ptr()
+        self.reset(db)
+        with torch.cuda.device(self.device):
+            rc = self.lib.brta_gibbs_run_batch(C.byref(cal), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _cabi.check(rc, 'brta_gibbs_run_batch (calibration)')
+        times = cyc.cpu().numpy().astype(np.float64)
+        if int(T['status'].max().item()) != 0:
+            raise _cabi.BrtaError('calibration launch failed (status != 0)')
+        self.reset(db)
+        return times
+
+    def _calibrate(self, db, costs, ticks, tick_offset, iters=None):
+        """Measured slicing.  The members of a team wait for the slowest one every iteration, and the
+        time a slice takes depends on more than the cost model knows (memoised rows built, label mix
+        behind the shared-memory reductions, co-resident CTAs).  So: run a few iterations with
+        ``task_cycles`` set, then move the slice boundaries inside every team so that the *measured*
+        time density is cut into equal parts.  Team sizes and CTA assignment stay (re-planning them
+        from measured chain costs was tried and lost: the measurement is only valid for the team
+        sizes it was taken with).  Results do not depend on the schedule."""
+        torch = self.torch
+        plan, T, H = db.plan, db.tensors, db.host
+        times = self._measure(db, CALIBRATE_ITERS if iters is None else int(iters))
+        tasks = plan.tasks
+        narrow = plan.cap_quads > plan.cap_units                    # chains at 8 B per quad
+        by_chain = [[] for _ in range(len(plan.team_size))]
+        for i, t in enumerate(tasks):
+            by_chain[int(t['chain'])].append(i)
+        for r, idx in enumerate(by_chain):
+            if len(idx) < 2:
+                continue
+            idx.sort(key=lambda i: int(tasks[i]['team_rank']))
+            last = tasks[idx[-1]]
+            bounds = np.array([int(tasks[i]['quad_begin']) for i in idx] + [int(last['quad_begin'] + last['quad_count'])])
+            weight = None
+            if costs is not None:
+                weight = np.full(int(bounds[-1]), COST_DIRECT)
+                for k in range(len(idx)):
+                    s0, e0 = int(bounds[k]), int(bounds[k + 1])
+                    weight[s0:s0 + costs[r].served(s0, e0)] = COST_SERVED
+            new = rebalance_team(bounds, np.maximum(times[idx], 1.0), weight, cap=int(plan.cap_quads[r]))
+            # per-iteration slice sums are accumulated in 32 bits inside a CTA
+            cs = np.concatenate(([0], np.cumsum(ticks[tick_offset[r]:tick_offset[r] + 4 * int(bounds[-1])], dtype=np.int64)))
+            hi = np.minimum(4 * new[1:], len(cs) - 1)
+            if np.any(cs[hi] - cs[4 * new[:-1]] >= (1 << 32)):
+                continue
+            for k, i in enumerate(idx):
+                tasks[i]['quad_begin'], tasks[i]['quad_count'] = int(new[k]), int(new[k + 1] - new[k])
+        units = np.where(narrow[tasks['chain']], (tasks['quad_count'] + 1) // 2, tasks['quad_count'])
+        plan.smem_units = int(units.max())
+        plan.slice_cap_quads = int(tasks['quad_count'].max())
+        assert plan.smem_units <= plan.cap_units
+        db.batch.slice_cap_quads = plan.smem_units
+        H['tasks'].copy_(torch.from_numpy(np.ascontiguousarray(tasks.view(np.int32).reshape(-1, 6))))
+        T['tasks'].copy_(H['tasks'], non_blocking=True)
+        torch.cuda.current_stream(T['tasks'].device).synchronize()
+        return times
 
     # ---- run -----------------------------------------------------------------------------
     def reset(self, db):

@@ -178,6 +178,49 @@ def build_plan(n_quads, grid, cap_quads, overhead_quads=DEFAULT_OVERHEAD_QUADS, 
                 est_efficiency=float(cost_q.sum()) / (grid * max(makespan, 1.0)))
 
 
+def density_from_times(bounds, times, quad_weight=None):
+    """Per-quad time density of one chain from measured slice times: inside slice i (quads
+    bounds[i] .. bounds[i+1]) the time ``times[i]`` is spread over the quads in proportion to
+    ``quad_weight`` (model cost per quad; uniform if None)."""
+    bounds = np.asarray(bounds, dtype=np.int64)
+    nq = int(bounds[-1])
+    w = np.ones(nq) if quad_weight is None else np.asarray(quad_weight, dtype=np.float64)
+    dens = np.empty(nq)
+    for i in range(len(bounds) - 1):
+        s, e = int(bounds[i]), int(bounds[i + 1])
+        dens[s:e] = w[s:e] * (float(times[i]) / w[s:e].sum())
+    return dens
+
+
+def cut_density(dens, c, cap=None):
+    """c+1 quad boundaries that cut a per-quad time density into c parts of equal time, every part
+    holding at least one quad.  Returns None if a part would exceed ``cap`` quads."""
+    nq = len(dens)
+    c = int(min(c, nq))
+    cum = np.cumsum(dens)
+    targets = cum[-1] * np.arange(1, c) / c
+    inner = np.searchsorted(cum, targets, side='left') + 1
+    new = np.concatenate(([0], inner, [nq])).astype(np.int64)
+    for i in range(1, c):                                    # strictly increasing, room for the rest
+        new[i] = min(max(new[i], new[i - 1] + 1), nq - (c - i))
+    if cap is not None and int(np.diff(new).max()) > int(cap):
+        return None
+    return new
+
+
+def rebalance_team(bounds, times, quad_weight=None, cap=None):
+    """New slice boundaries of one team from the measured times of its current slices (same team
+    size): the measured time density is cut into equal parts.  Falls back to the old boundaries
+    if a slice would exceed ``cap`` quads or the measurement is unusable."""
+    bounds = np.asarray(bounds, dtype=np.int64)
+    times = np.asarray(times, dtype=np.float64)
+    c = len(bounds) - 1
+    if c < 2 or int(bounds[-1]) < 2 * c or not np.all(times > 0):
+        return bounds.copy()
+    new = cut_density(density_from_times(bounds, times, quad_weight), c, cap)
+    return bounds.copy() if new is None else new
+
+
 def shard_chains(costs, n_shards):
     """Longest-processing-time-first assignment of whole chains to GPUs (no collective:
     chains are independent, basicrta/gibbs.py:73-86).  Returns a list of index arrays."""

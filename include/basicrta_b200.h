@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BRTA_ABI_VERSION 1
+#define BRTA_ABI_VERSION 2
 
 /* compile-time geometry of the sampler kernel */
 #ifndef BRTA_THREADS
@@ -180,6 +180,12 @@ typedef struct brta_batch {
     void*            exchange;     /* zeroed by the caller; chain r owns BRTA_EXCH_BYTES(team_size)
                                       bytes at exch_offset[r]                             */
     const int64_t*   exch_offset;  /* [R] byte offsets, multiples of 128                 */
+
+    /* schedule feedback (may be NULL): task i gets the clock cycles its CTA spent from the start of an
+     * iteration to the post of its partial statistics, summed over the second half of the iterations
+     * (the first ones start from the initial state and are not typical).  A short launch
+     * with this set tells the scheduler how long each slice really takes (see engine.calibrate). */
+    uint64_t*        task_cycles;  /* [number of tasks]                                  */
 } brta_batch;
 
 /* Device capabilities.  Python side: Gibbs.run needs it to size the schedule. */

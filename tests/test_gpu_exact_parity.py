@@ -84,6 +84,35 @@ def test_team_size_does_not_change_results(engine):
     np.testing.assert_array_equal(got.indicator, ref['indicator'])
 
 
+def test_measured_slicing_changes_the_schedule_not_the_results(engine):
+    """engine._calibrate times every slice in a short launch and moves the slice boundaries inside the
+    teams; Philox is keyed by the datum, statistics are integers: the output must not change by a bit."""
+    rng = np.random.default_rng(12)
+    chains = []
+    for r, n in enumerate((30000, 9000, 52001, 700)):
+        comp = rng.choice(3, size=n, p=[0.8, 0.15, 0.05])
+        x = rng.exponential(1.0 / np.array([4.0, 0.1, 0.002])[comp])
+        chains.append(ChainInput(ticks=np.maximum(np.ceil(x / 0.1), 1).astype(np.int64), ts=0.1, chain_id=40 + r))
+    K, niter, thin = 15, 60, 20
+    plain = engine.prepare(chains, K, niter, thin=thin, seed=5, calibrate=False)
+    tuned = engine.prepare(chains, K, niter, thin=thin, seed=5, calibrate=True)
+    t0, t1 = plain.plan.tasks, tuned.plan.tasks
+    assert len(t0) == len(t1) and np.array_equal(t0['chain'], t1['chain']) and np.array_equal(t0['team_rank'], t1['team_rank'])
+    assert not np.array_equal(t0['quad_begin'], t1['quad_begin'])          # boundaries moved
+    for r, ch in enumerate(chains):                                        # and still tile every chain
+        mine = np.sort(t1[t1['chain'] == r], order='team_rank')
+        assert mine['quad_begin'][0] == 0 and np.all(mine['quad_count'] >= 1)
+        assert np.array_equal(mine['quad_begin'][1:], (mine['quad_begin'] + mine['quad_count'])[:-1])
+        assert mine['quad_begin'][-1] + mine['quad_count'][-1] == (len(ch.ticks) + 3) // 4
+    engine.launch(plain)
+    engine.launch(tuned)
+    for a, b in zip(engine.fetch(plain), engine.fetch(tuned)):
+        assert a.status == 0 and b.status == 0
+        np.testing.assert_array_equal(a.mcweights, b.mcweights)
+        np.testing.assert_array_equal(a.mcrates, b.mcrates)
+        np.testing.assert_array_equal(a.indicator, b.indicator)
+
+
 def test_fast_mode_flip_rate(engine):
     """FAST (MUFU.EX2 + FMA contraction) differs from EXACT only where a uniform lands within
     float rounding of a CDF boundary: < 1e-4 of the labels, and the statistics stay close."""

@@ -64,6 +64,38 @@ def test_plan_rejects_bad_input():
         build_plan([10 ** 6], 4, 100)                        # does not fit 4 CTAs x 100 quads
 
 
+def test_rebalance_team_equalises_measured_times():
+    """Measured slicing (engine._calibrate): cutting the measured time density into equal parts
+    converges to slices of equal time even when the cost model (uniform here) is wrong."""
+    from basicrta_b200.plan import cut_density, density_from_times, rebalance_team
+    nq, c = 4000, 7
+    true = np.where(np.arange(nq) < 1500, 1.0, 3.0) + 0.5 * np.sin(np.arange(nq) / 300.0)
+    cum = np.concatenate(([0.0], np.cumsum(true)))
+
+    def measure(b):
+        return cum[b[1:]] - cum[b[:-1]] + 40.0             # + a fixed per-slice overhead
+
+    bounds = np.linspace(0, nq, c + 1).astype(np.int64)
+    spread0 = np.ptp(measure(bounds)) / measure(bounds).mean()
+    for _ in range(3):
+        bounds = rebalance_team(bounds, measure(bounds))
+        assert bounds[0] == 0 and bounds[-1] == nq and np.all(np.diff(bounds) >= 1)
+    t = measure(bounds)
+    assert spread0 > 0.8 and np.ptp(t) / t.mean() < 0.05
+    # a slice longer than the shared memory allows: the old boundaries stay
+    eq = np.linspace(0, nq, c + 1).astype(np.int64)
+    np.testing.assert_array_equal(rebalance_team(eq, measure(eq), cap=600), eq)
+    # unusable measurements and degenerate teams: unchanged
+    np.testing.assert_array_equal(rebalance_team(eq, np.zeros(c)), eq)
+    np.testing.assert_array_equal(rebalance_team([0, 5], [3.0]), [0, 5])
+    np.testing.assert_array_equal(rebalance_team([0, 1, 2, 3], [5.0, 1.0, 1.0]), [0, 1, 2, 3])
+    # model weights shape the density inside a slice
+    d = density_from_times([0, 4], [8.0], quad_weight=[1, 1, 3, 3])
+    np.testing.assert_allclose(d, [1, 1, 3, 3])
+    np.testing.assert_array_equal(cut_density(d, 2), [0, 3, 4])
+    assert cut_density(np.ones(10), 2, cap=4) is None
+
+
 def test_shard_chains_lpt():
     costs = np.array([100, 90, 50, 40, 30, 20, 10, 5])
     shards = shard_chains(costs, 3)

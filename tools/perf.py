@@ -35,7 +35,7 @@ cps = os.environ.get('BRTA_CTAS_PER_SM')
 nw = os.environ.get('BRTA_WAVES')
 ov = os.environ.get('BRTA_OVERHEAD')
 eng = GibbsEngine(0, ctas_per_sm=int(cps) if cps else None, overhead_quads=float(ov) if ov else None)
-db = eng.prepare(chains, 15, niter, thin=100, seed=1, n_waves=int(nw) if nw else None,
+db = eng.prepare(chains, 15, niter, thin=100, seed=1, n_waves=int(nw) if nw else None, calibrate=bool(int(os.environ.get('BRTA_CALIBRATE', '0'))),
                  flags=_cabi.FLAG_NO_TABLE if 'notable' in sys.argv else 0)
 p = db.plan
 best = 1e30

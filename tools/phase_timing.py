@@ -28,7 +28,7 @@ from basicrta_b200.engine import GibbsEngine
 cps = os.environ.get('BRTA_CTAS_PER_SM')
 eng = GibbsEngine(0, ctas_per_sm=int(cps) if cps else None)
 nw = os.environ.get('BRTA_WAVES')
-db = eng.prepare(chains, K, niter, thin=100, seed=1, n_waves=int(nw) if nw else None)
+db = eng.prepare(chains, K, niter, thin=100, seed=1, n_waves=int(nw) if nw else None, calibrate=bool(int(os.environ.get('BRTA_CALIBRATE', '0'))))
 print('waves', db.plan.n_waves, 'est eff', round(db.plan.est_efficiency, 3))
 buf = torch.zeros(db.plan.grid * 8, dtype=torch.int64, device='cuda')
 lib = _cabi.load()
@@ -64,3 +64,17 @@ try:
           f'(ratio served/recomputed = {coef[0] / coef[1]:.3f}); served share {A[:, 0].sum() / A[:, :2].sum():.3f}')
 except Exception as e:
     print('regression failed:', e)
+
+# within-team spread of the sweep phase (single-wave plans: one task per CTA)
+if db.plan.n_waves == 1:
+    allph = buf.cpu().numpy().reshape(-1, 8).astype(np.float64) / niter
+    spread, wait = [], []
+    for r in range(len(chains)):
+        ctas = [b for b in range(db.plan.grid) if len(db.plan.tasks_of_cta(b)) and db.plan.tasks_of_cta(b)[0]['chain'] == r]
+        sw = allph[ctas, 0]
+        spread.append((sw.max() - sw.min()) / sw.mean())
+        wait.append((sw.max() - sw.mean()))
+    print(f'within-team sweep spread (max-min)/mean: median {np.median(spread):.2f}, max {np.max(spread):.2f}; '
+          f'mean wait for the slowest member {np.mean(wait):.0f} cyc/iter')
+    tm = np.array([allph[[b for b in range(db.plan.grid) if len(db.plan.tasks_of_cta(b)) and db.plan.tasks_of_cta(b)[0]['chain'] == r], 0].max() for r in range(len(chains))])
+    print(f'slowest-member sweep per team: min {tm.min():.0f} mean {tm.mean():.0f} max {tm.max():.0f} cyc/iter')
