@@ -642,6 +642,10 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
+    // The warp that runs the serial part of an iteration (partials, posterior).  Warp w of every CTA sits on
+    // SM sub-partition w % 4; rotating the role over the co-resident CTAs (blockIdx b, b + grid/4, ... or
+    // 4m .. 4m+3, whichever the block scheduler chose) spreads the serial work over the four schedulers.
+    const int lead = (int)((blockIdx.x + blockIdx.x / max(gridDim.x >> 2, 1u)) & (WARPS - 1));
     const uint32_t key0 = (uint32_t)b.seed;
     const uint32_t key1 = (uint32_t)(b.seed >> 32);
     const int kreal = b.ncomp;
@@ -724,7 +728,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
         unsigned slice_n = 0;
         unsigned long long slice_t = 0;
         float wh = 0.0f, rh_a = 1.0f, rh_b = 1.0f;
-        if (warp == 0) {
+        if (warp == lead) {
 #pragma unroll
             for (int w = 0; w < WARPS; ++w) { slice_n += s_red_n[w]; slice_t += s_red_t[w]; }
         }
@@ -793,7 +797,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
             if (b.task_cycles && 2 * j > niter) busy_cycles += (unsigned long long)(clock64() - iter_t0);
 
             // ---- this CTA's partials; the uncounted dominant label follows by subtraction --
-            if (warp == 0) {
+            if (warp == lead) {
                 unsigned cnt = s_cnt[lane];
                 unsigned sum = s_sum[lane];
                 s_cnt[lane] = 0;
@@ -966,7 +970,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
                 }
                 PHASE_MARK(5);                             // gamma trials
                 __syncthreads();
-                if (warp == 0) {
+                if (warp == lead) {
                     if (trace && task.team_rank == 0 && live) {
                         const size_t o = ((size_t)r * niter + (j - 1)) * kreal + lane;
                         b.trace_nk[o] = (int64_t)cnt;

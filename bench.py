@@ -45,12 +45,13 @@ UNIT = 'N*K*iter/s'
 
 
 # ---- synthetic workload ---------------------------------------
-def residue_times(r):
+def residue_times(r, seed_offset=0, n_scale=1.0):
     """Residue r of C2: seed 1000+r; N = round(10^U(4,5)); 2-4 true components with rates
     log-uniform in [1e-3, 10] /ns separated by >= x5; weights ~ Dirichlet(1) sorted so the
-    fastest rate has the largest weight; ceil-quantised to the 0.1 ns grid."""
-    rng = np.random.default_rng(1000 + r)
-    n = int(round(10 ** rng.uniform(4, 5)))
+    fastest rate has the largest weight; ceil-quantised to the 0.1 ns grid.  C3 (the same
+    residues at five contact cutoffs) shifts the seed by 10 000 per cutoff and scales N."""
+    rng = np.random.default_rng(1000 + r + seed_offset)
+    n = int(round(n_scale * 10 ** rng.uniform(4, 5)))
     m = int(rng.integers(2, 5))
     while True:
         rates = np.sort(10 ** rng.uniform(-3, 1, size=m))[::-1]

@@ -22,33 +22,23 @@ def synth(rng, n, rates, weights, ts=0.1):
 
 
 def configs():
-    rng = np.random.default_rng(7)
-    # C1: one residue, three exponentials, N = 5 000
-    yield 'C1 single residue N=5e3 K=15', 15, [synth(rng, 5000, [5, 0.05, 0.001], [0.9, 0.09, 0.01])]
-    # C2: the bench workload
-    c2 = bench.workload(range(bench.N_RESIDUES))
-    yield 'C2 400 residues K=15', 15, c2
-    # C3: the same residues at five contact cutoffs -- a larger cutoff keeps more (and longer) contacts
-    c3 = []
-    for f in (0.6, 0.8, 1.0, 1.25, 1.5):
-        for t in c2:
-            keep = max(64, int(len(t) * min(f, 1.0)))
-            c3.append(np.maximum(1, np.rint(t[:keep] * max(f, 1.0)).astype(np.int64)))
+    """The synthetic inputs of SURVEY.md 8(d)."""
+    c1 = [0.90, 0.09, 0.01], [5, 0.05, 0.001]
+    yield 'C1 single residue N=5e3 K=15', 15, [synth(np.random.default_rng(20241109), 5000, c1[1], c1[0])]
+    yield 'C2 400 residues K=15', 15, bench.workload(range(bench.N_RESIDUES))
+    c3 = [bench.residue_times(r, seed_offset=10000 * c, n_scale=f)
+          for c, f in enumerate((0.6, 0.8, 1.0, 1.25, 1.5)) for r in range(bench.N_RESIDUES)]
     yield 'C3 2000 chains (5 cutoffs) K=15', 15, c3
-    # C4 on one GPU: one giant chain
-    yield 'C4 giant residue N=1e6 K=15 (1 GPU)', 15, [synth(rng, 1_000_000, [5, 0.5, 0.05, 0.005], [0.6, 0.25, 0.1, 0.05])]
-    # C5: K = 30, true rates over four decades, 100 residues
-    c5 = []
-    for r in range(100):
-        n = int(round(10 ** rng.uniform(4, 5)))
-        c5.append(synth(rng, n, [10, 1, 0.1, 0.01, 0.001], [0.5, 0.25, 0.15, 0.07, 0.03]))
-    yield 'C5 100 residues K=30, rates over 4 decades', 30, c5
+    yield 'C4 giant residue N=1e6 K=15 (1 GPU)', 15, [synth(np.random.default_rng(4), 1_000_000, c1[1], c1[0])]
+    c5 = [synth(np.random.default_rng(5000 + r), 20000, [10, 1, 0.1, 0.01, 0.001], [0.6, 0.25, 0.1, 0.04, 0.01])
+          for r in range(100)]
+    yield 'C5 100 residues N=2e4 K=30, rates over 4 decades', 30, c5
 
 
 eng = GibbsEngine(0)
 for name, K, ticks in configs():
     chains = [ChainInput(ticks=t, ts=0.1, chain_id=i) for i, t in enumerate(ticks)]
-    db = eng.prepare(chains, K, niter, thin=100, seed=1)
+    db = eng.prepare(chains, K, niter, thin=100, seed=1, calibrate=True)
     best = 1e30
     for rep in range(3):
         eng.reset(db)
