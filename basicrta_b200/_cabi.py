@@ -11,6 +11,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('BRTA_LIB', os.path.join(HERE, 'libbrta_gibbs.so'))   # BRTA_LIB: developer override
 SRC = os.path.join(HERE, 'csrc', 'brta_gibbs.cu')
+SRC_PINDICATOR = os.path.join(HERE, 'csrc', 'brta_pindicator.cu')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
 ABI_VERSION = 2
@@ -84,7 +85,8 @@ class Batch(C.Structure):
 
 
 EXPORTS = ('brta_abi_version', 'brta_last_error', 'brta_query', 'brta_gibbs_launch_info',
-           'brta_gibbs_run_batch', 'brta_philox_fill', 'brta_mufu_probe', 'brta_enable_peer_access')
+           'brta_gibbs_run_batch', 'brta_philox_fill', 'brta_mufu_probe', 'brta_enable_peer_access',
+           'brta_pindicator_counts')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-shared', '-Xcompiler', '-fPIC']
@@ -92,12 +94,12 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', 
 
 def build(force=False, verbose=False):
     """Compile ``csrc/brta_gibbs.cu`` for sm_100a into ``libbrta_gibbs.so`` (in-tree)."""
-    srcs = [SRC] + [os.path.join(HERE, 'csrc', f) for f in ('brta_math.cuh', 'brta_rng.cuh')] + \
+    srcs = [SRC, SRC_PINDICATOR] + [os.path.join(HERE, 'csrc', f) for f in ('brta_math.cuh', 'brta_rng.cuh', 'brta_host.h')] + \
            [os.path.join(INCLUDE, 'basicrta_b200.h')]
     if (not force and os.path.exists(LIB_PATH) and
             all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
         return LIB_PATH
-    cmd = ['nvcc'] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH, SRC]
+    cmd = ['nvcc'] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH, SRC, SRC_PINDICATOR]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise BrtaError('nvcc failed:\n' + res.stdout + res.stderr)
@@ -127,6 +129,8 @@ def load():
                                      C.c_uint32, C.c_uint64, C.c_void_p]
     lib.brta_enable_peer_access.argtypes = [C.c_int, C.c_int]
     lib.brta_mufu_probe.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.brta_pindicator_counts.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                           C.c_int32, C.c_void_p, C.c_void_p]
     for name in EXPORTS:
         getattr(lib, name)
     if lib.brta_abi_version() != ABI_VERSION:

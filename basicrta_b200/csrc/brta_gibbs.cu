@@ -31,6 +31,7 @@
 #include <string.h>
 
 #include "../../include/basicrta_b200.h"
+#include "brta_host.h"
 #include "brta_math.cuh"
 #include "brta_rng.cuh"
 
@@ -1065,7 +1066,7 @@ __global__ void __launch_bounds__(256) mufu_probe_kernel(float* sink, int iters)
 // ---- host side ----------------------------------------------------------------------
 thread_local char g_err[512] = "";
 
-int fail(int code, const char* fmt, const char* detail = "")
+int fail(int code, const char* fmt, const char* detail)
 {
     snprintf(g_err, sizeof(g_err), fmt, detail);
     return code;

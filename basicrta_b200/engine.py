@@ -561,6 +561,44 @@ def run_sharded(chain, ncomp, niter, devices, thin=100, seed=0, flags=0, inject=
 _engines = {}
 
 
+def pindicator_counts(indicator, cluster_of, n_clusters, device=0):
+    """Cluster-membership counts of every datum (the accumulation loop of
+    ``Gibbs.cluster``, basicrta/gibbs.py:264-268) on the GPU.
+
+    ``indicator``: uint8 [S, N] label rows -- a NumPy array (copied to the device) or a CUDA
+    tensor (used in place, e.g. a view of the sampler's ``indicator`` output that never left the GPU);
+    ``cluster_of``: int8 [S, K], the mixture label of (row, component) or -1 if that pair is below the
+    weight cutoff.  Returns int32 counts [N, n_clusters] as a NumPy array."""
+    torch = _torch()
+    lib = _cabi.load()
+    dev = torch.device('cuda', int(device))
+    if isinstance(indicator, np.ndarray):
+        if indicator.dtype != np.uint8 or indicator.ndim != 2:
+            raise ValueError('indicator must be uint8 [S, N]')
+        ind = torch.from_numpy(np.ascontiguousarray(indicator)).to(dev, non_blocking=True)
+    else:
+        ind = indicator
+        if ind.dtype != torch.uint8 or ind.dim() != 2 or ind.stride(1) != 1 or ind.device != dev:
+            raise ValueError(f'indicator must be a uint8 [S, N] tensor with unit column stride on {dev}')
+    n_rows, n_data = int(ind.shape[0]), int(ind.shape[1])
+    cmap = np.ascontiguousarray(cluster_of, dtype=np.int8)
+    if cmap.ndim != 2 or cmap.shape[0] != n_rows:
+        raise ValueError('cluster_of must be int8 [S, K] with one row per indicator row')
+    if not 1 <= int(n_clusters) <= 32:
+        raise ValueError('n_clusters must be in 1..32')
+    counts = torch.zeros((n_data, int(n_clusters)), dtype=torch.int32, device=dev)
+    if n_rows == 0 or n_data == 0:
+        return counts.cpu().numpy()
+    cmap_d = torch.from_numpy(cmap).to(dev)
+    with torch.cuda.device(dev):
+        rc = lib.brta_pindicator_counts(C.c_void_p(ind.data_ptr()), int(ind.stride(0)) if n_rows > 1 else max(n_data, 1),
+                                        n_rows, n_data, C.c_void_p(cmap_d.data_ptr()), int(cmap.shape[1]),
+                                        int(n_clusters), C.c_void_p(counts.data_ptr()),
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _cabi.check(rc, 'brta_pindicator_counts')
+    return counts.cpu().numpy()
+
+
 def get_engine(device=0):
     if device not in _engines:
         _engines[device] = GibbsEngine(device)

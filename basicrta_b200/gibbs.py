@@ -158,9 +158,9 @@ class Gibbs(object):
         from . import postprocess
         return postprocess.cluster(self, method=method, **kwargs)
 
-    def process_gibbs(self, save=True):
+    def process_gibbs(self, save=True, device=None):
         from . import postprocess
-        return postprocess.process_gibbs(self, save=save)
+        return postprocess.process_gibbs(self, save=save, device=device)
 
     def estimate_tau(self):
         from . import postprocess

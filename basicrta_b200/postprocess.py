@@ -29,9 +29,10 @@ def _mode(values):
     return stats.mode(values).mode
 
 
-def cluster(gibbs, method='GaussianMixture', **kwargs):
+def cluster(gibbs, method='GaussianMixture', device=None, **kwargs):
     """Cluster the retained (weight, rate) samples in log space and accumulate, per datum,
-    how often its label fell in each cluster (gibbs.py:221-273)."""
+    how often its label fell in each cluster (gibbs.py:221-273).  ``device``: GPU index to run the
+    accumulation on (``engine.pindicator_counts``, same integers); None keeps it in NumPy."""
     from sklearn import mixture
 
     burn, wcutoff, weights, rates, keep = _filtered(gibbs)
@@ -47,19 +48,29 @@ def cluster(gibbs, method='GaussianMixture', **kwargs):
     labels = model.predict(np.log(data))
 
     indicator = gibbs.indicator[burn:] if gibbs.indicator is not None else gibbs._sample_indicator()
-    pind = np.zeros((gibbs.times.shape[0], lmode))
-    # pind[i, cluster] += 1 for every retained (row, component) whose component labels datum i
-    lut = np.full((indicator.shape[0], 256), -1, dtype=np.int16)
-    lut[rows, comps] = labels
-    for lo in range(0, indicator.shape[0], 64):                                   # bounded scratch
-        mapped = np.take_along_axis(lut[lo:lo + 64], indicator[lo:lo + 64].astype(np.int64), axis=1)
-        for c in range(lmode):
-            pind[:, c] += (mapped == c).sum(axis=0)
+    pind = pindicator_counts_host(indicator, rows, comps, labels, lmode, gibbs.ncomp, device).astype(np.float64)
     with np.errstate(invalid='ignore', divide='ignore'):
         pind = (pind.T / pind.sum(axis=1)).T
     gibbs.processed_results.indicator = pind
     gibbs.processed_results.labels = labels
     return labels
+
+
+def pindicator_counts_host(indicator, rows, comps, labels, n_clusters, ncomp, device=None):
+    """counts[i, c] = number of retained (row, component) pairs with mixture label c whose component
+    labels datum i in that row (gibbs.py:264-268).  NumPy, or the GPU kernel if ``device`` is given."""
+    ncomp = max(int(ncomp), int(indicator.max(initial=0)) + 1)
+    lut = np.full((indicator.shape[0], ncomp), -1, dtype=np.int8)
+    lut[rows, comps] = labels
+    if device is not None:
+        from .engine import pindicator_counts
+        return pindicator_counts(indicator, lut, n_clusters, device=device)
+    counts = np.zeros((indicator.shape[1], n_clusters), dtype=np.int64)
+    for lo in range(0, indicator.shape[0], 64):                                   # bounded scratch
+        mapped = np.take_along_axis(lut[lo:lo + 64], indicator[lo:lo + 64].astype(np.int64), axis=1)
+        for c in range(n_clusters):
+            counts[:, c] += (mapped == c).sum(axis=0)
+    return counts
 
 
 def sort_labels(gibbs):
@@ -80,14 +91,14 @@ def sort_labels(gibbs):
     return sorts[labels], presorts
 
 
-def process_gibbs(gibbs, save=True):
-    """gibbs.py:275-308 without figures."""
+def process_gibbs(gibbs, save=True, device=None):
+    """gibbs.py:275-308 without figures.  ``device``: see :func:`cluster`."""
     burn, wcutoff, weights, rates, keep = _filtered(gibbs)
     rows, comps = np.where(keep)
     iteration = np.arange(gibbs.burnin, gibbs.niter + 1, gibbs.g)[rows] // gibbs.g
     lmode = int(_mode(keep.sum(axis=1)))
 
-    cluster(gibbs, n_init=117, n_components=lmode)
+    cluster(gibbs, n_init=117, n_components=lmode, device=device)
     labels, presorts = sort_labels(gibbs)
     pr = gibbs.processed_results
     pr.labels = labels

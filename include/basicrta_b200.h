@@ -216,6 +216,19 @@ int brta_enable_peer_access(int device, int peer);
  * sink_dev: blocks*256 floats (never written in practice). */
 int brta_mufu_probe(float* sink_dev, int blocks, int iters, void* stream);
 
+/* Cluster membership counts of every datum from the stored label rows -- the accumulation of
+ * Gibbs.cluster (basicrta/gibbs.py:264-268): for every row j < n_rows and datum i < n_data,
+ *     c = cluster_of[j * ncomp + indicator[j * row_stride + i]];  if (c >= 0) counts[i * n_clusters + c] += 1;
+ * indicator: uint8 rows of row_stride >= n_data bytes (the `indicator` of brta_batch, or a copy of
+ * Gibbs.indicator[burnin/g:]); cluster_of: int8 [n_rows, ncomp], -1 for (row, component) pairs below the
+ * weight cutoff (gibbs.py:233, 247), else the mixture label (gibbs.py:257); counts: int32
+ * [n_data, n_clusters], ADDED to (zero it first).  All pointers are device pointers.  The caller
+ * normalises the rows (gibbs.py:270). */
+#define BRTA_PINDICATOR_MAX_CLUSTERS 32
+int brta_pindicator_counts(const uint8_t* indicator, int64_t row_stride, int32_t n_rows, int32_t n_data,
+                           const int8_t* cluster_of, int32_t ncomp, int32_t n_clusters,
+                           int32_t* counts, void* stream);
+
 /* Last error message of the calling thread ("" if none). */
 const char* brta_last_error(void);
 

@@ -70,6 +70,12 @@ def test_argument_errors_do_not_need_a_gpu():
     b.ncomp = 99
     assert lib.brta_gibbs_run_batch(C.byref(b), None) == -2               # BRTA_E_NCOMP
     assert lib.brta_query(0, None) == -1
+    assert lib.brta_pindicator_counts(None, 0, 0, 0, None, 1, 1, None, None) == -1
+    one = C.c_int(0)
+    p = C.cast(C.byref(one), C.c_void_p)
+    assert lib.brta_pindicator_counts(p, 4, 2, 8, p, 15, 3, p, None) == -3   # row_stride < n_data: BRTA_E_RANGE
+    assert lib.brta_pindicator_counts(p, 8, 2, 8, p, 15, 33, p, None) == -2  # n_clusters > 32
+    assert lib.brta_pindicator_counts(p, 8, 0, 8, p, 15, 3, p, None) == 0    # nothing to do
 
 
 def test_product_fails_loudly_without_cuda():
