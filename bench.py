@@ -275,7 +275,11 @@ def run_b200_arm(args):
         raise SystemExit('weights do not sum to one: the kernel did not run correctly')
 
     t = torch.tensor([ms, e2e_ms, float(h2d_bytes), float(d2h_bytes)], dtype=torch.float64, device=f'cuda:{local}')
+    per_rank_ms = [ms / args.steps]
     if world > 1:
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        per_rank_ms = [float(g[0]) / args.steps for g in gathered]
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
@@ -306,6 +310,7 @@ def run_b200_arm(args):
                     'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes,
                     'ms_per_step': e2e_ms / args.steps},
             'gpu_launches': args.steps * world,
+            'per_rank_ms_per_step': [round(x, 3) for x in per_rank_ms],
             'roofline': {'bound': 'mufu', 'achieved': per_gpu / 1e9, 'peak': peak / 1e9, 'unit': 'G ex2/s',
                          'frac': per_gpu / peak, 'traffic': None,
                          'executed_ex2_share': db.executed_ex2_share,
