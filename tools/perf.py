@@ -24,6 +24,12 @@ if nd:
         comp = rng.choice(3, size=nd[0], p=[0.9, 0.09, 0.01])
         x = rng.exponential(1.0 / np.array([5, 0.05, 0.001])[comp])
         ticks.append(np.maximum(np.ceil(x / 0.1), 1).astype(np.int64))
+elif any(a.startswith('shard=') for a in sys.argv):      # shard=G:r -> what rank r of G GPUs gets from bench.py
+    from basicrta_b200.plan import shard_chains
+    G, r = (int(x) for x in [a for a in sys.argv if a.startswith('shard=')][0][6:].split(':'))
+    full = bench.workload(range(bench.N_RESIDUES))
+    ticks = [full[i] for i in shard_chains(np.array([len(t) for t in full]), G)[r]]
+    n_chains = len(ticks)
 else:
     ticks = bench.workload(range(n_chains))
 chains = [ChainInput(ticks=t, ts=0.1, chain_id=i) for i, t in enumerate(ticks)]
