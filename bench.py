@@ -162,6 +162,21 @@ class ClockSampler:
 
 
 # ---- B200 arm ----------------------------------------------------------------------------------
+def profiled_traffic(n_res, niter, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the sweep kernel on the default
+    workload, from the committed ncu capture (profiles/README.md); None for any other workload."""
+    path = os.path.join(ROOT, 'profiles', 'r1e_dram_bytes_bench.csv')
+    if (n_res, niter, world) != (N_RESIDUES, NITER, 1) or not os.path.exists(path):
+        return None
+    total = 0
+    with open(path) as f:
+        for row in f:
+            cells = [c.strip('"') for c in row.strip().split('","')]
+            if len(cells) > 3 and cells[-3] in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+                total += int(cells[-1])
+    return float(total) if total else None
+
+
 def measure_mufu_peak(torch, lib, device, sm_count):
     """ex2/s the chip sustains (brta_mufu_probe): 8 resident CTAs of 256 threads per SM."""
     import ctypes as C
@@ -312,7 +327,9 @@ def run_b200_arm(args):
             'gpu_launches': args.steps * world,
             'per_rank_ms_per_step': [round(x, 3) for x in per_rank_ms],
             'roofline': {'bound': 'mufu', 'achieved': per_gpu / 1e9, 'peak': peak / 1e9, 'unit': 'G ex2/s',
-                         'frac': per_gpu / peak, 'traffic': None,
+                         'frac': per_gpu / peak, 'traffic': profiled_traffic(n_res, niter, world),
+                         'traffic_unit': 'bytes per launch (ncu dram read + write, profiles/r1e_dram_bytes_bench.csv); '
+                                         f'algorithmic: {algo_bytes:.4g}',
                          'executed_ex2_share': db.executed_ex2_share,
                          'note': 'per GPU; algorithmic unit = 1 ex2 per (datum, component) pair per iteration (SURVEY 8d); '
                                  'peak = brta_mufu_probe measured in this run (nominal 148 SM x 16/clk x 1.965 GHz = 4654 G/s). '
