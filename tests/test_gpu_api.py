@@ -183,3 +183,42 @@ def test_chain_sharded_over_two_gpus_is_bit_exact():
     assert two.status == 0
     assert np.array_equal(one.mcrates, two.mcrates) and np.array_equal(one.mcweights, two.mcweights)
     assert np.array_equal(one.indicator, two.indicator)
+
+
+def test_full_size_batch_invariants(engine):
+    """BASELINE.json's sizes are out of the oracle's reach, so the full-size checks are properties that do
+    not depend on size: every iteration's component counts add up to N and its tick sums to the chain's
+    total (a checksum of checksums over the integer statistics); the stored label rows reproduce the
+    traced counts; the launch is deterministic; and neither the batch a chain runs in nor the schedule
+    (waves, measured slicing) changes one bit of its output.  Sizes: the C2 range (1e4 .. 1e5 data),
+    K = 15, free-running FAST mode."""
+    import bench
+    ids = [22, 385, 74, 329, 231, 5]                       # N from 1.0e4 to 1.0e5
+    ticks = bench.workload(ids)
+    assert max(len(t) for t in ticks) > 90000 and min(len(t) for t in ticks) < 16000
+    chains = [ChainInput(ticks=t, ts=0.1, chain_id=i) for i, t in zip(ids, ticks)]
+    K, niter, thin = 15, 400, 100
+    first = engine.run(chains, K, niter, thin=thin, seed=77, flags=_cabi.FLAG_TRACE)
+    for ch, res in zip(chains, first):
+        n = len(ch.ticks)
+        assert res.status == 0
+        assert np.array_equal(res.trace_nk.sum(axis=1), np.full(niter, n))
+        assert np.array_equal(res.trace_tk.sum(axis=1), np.full(niter, int(np.sum(ch.ticks))))
+        for row in range(niter // thin):
+            hist = np.bincount(res.indicator[row], minlength=K)
+            assert np.array_equal(hist, res.trace_nk[(row + 1) * thin - 1])
+            tsum = np.bincount(res.indicator[row], weights=ch.ticks, minlength=K)
+            assert np.array_equal(tsum.astype(np.int64), res.trace_tk[(row + 1) * thin - 1])
+        assert np.allclose(res.mcweights.sum(axis=1), 1.0, atol=1e-5) and (res.mcrates > 0).all()
+    again = engine.run(chains, K, niter, thin=thin, seed=77, flags=_cabi.FLAG_TRACE)
+    waves3 = engine.run(chains, K, niter, thin=thin, seed=77, n_waves=3)
+    alone = engine.run(chains[1:2], K, niter, thin=thin, seed=77)
+    db = engine.prepare(chains, K, niter, thin=thin, seed=77, calibrate=True)
+    engine.launch(db)
+    tuned = engine.fetch(db)
+    for a, b, c, d in zip(first, again, waves3, tuned):
+        for other in (b, c, d):
+            assert np.array_equal(a.mcweights, other.mcweights) and np.array_equal(a.mcrates, other.mcrates)
+            assert np.array_equal(a.indicator, other.indicator)
+        assert np.array_equal(a.trace_nk, b.trace_nk)
+    assert np.array_equal(first[1].indicator, alone[0].indicator) and np.array_equal(first[1].mcrates, alone[0].mcrates)
