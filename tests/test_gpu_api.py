@@ -222,3 +222,25 @@ def test_full_size_batch_invariants(engine):
             assert np.array_equal(a.indicator, other.indicator)
         assert np.array_equal(a.trace_nk, b.trace_nk)
     assert np.array_equal(first[1].indicator, alone[0].indicator) and np.array_equal(first[1].mcrates, alone[0].mcrates)
+
+
+def test_many_chains_per_launch(engine):
+    """Config C3 in miniature: far more chains than CTAs (several waves, every CTA walks a list of tasks).
+    Each chain's output equals what it produces when launched on its own."""
+    rng = np.random.default_rng(31)
+    chains = []
+    for r in range(1500):
+        n = int(rng.integers(40, 2500))
+        comp = rng.choice(2, size=n, p=[0.85, 0.15])
+        x = rng.exponential(1.0 / np.array([3.0, 0.05])[comp])
+        chains.append(ChainInput(ticks=np.maximum(np.ceil(x / 0.1), 1).astype(np.int64), ts=0.1, chain_id=r))
+    K, niter, thin = 5, 120, 40
+    db = engine.prepare(chains, K, niter, thin=thin, seed=3)
+    assert db.plan.n_waves >= 2 and len(db.plan.tasks) >= 1500
+    engine.launch(db)
+    res = engine.fetch(db)
+    assert all(x.status == 0 for x in res)
+    for r in (0, 1, 613, 1499):
+        solo = engine.run([chains[r]], K, niter, thin=thin, seed=3)[0]
+        assert np.array_equal(solo.indicator, res[r].indicator)
+        assert np.array_equal(solo.mcweights, res[r].mcweights) and np.array_equal(solo.mcrates, res[r].mcrates)
