@@ -5,26 +5,35 @@
 //
 //   * a chain (residue) is owned by a *team* of CTAs chosen by the host schedule
 //     (basicrta_b200/plan.py); each CTA keeps its slice of the residence times in shared
-//     memory as float ticks for the whole run (times are integer multiples of ts,
-//     basicrta/contacts.py:222-229);
+//     memory for the whole run, as the integer ticks they are (times are integer multiples
+//     of ts, basicrta/contacts.py:222-229): 2 B per datum if the chain's ticks fit 16 bits;
+//   * the host passes a chain in ascending-tick order (labels go back through `perm`).  Once
+//     per iteration the CTA builds the K cumulative sums  sum_{k'<=k} 2^(c_k' - a_k' tick)
+//     for every tick value of a window of its slice ("memoised rows", shared memory);
 //   * per iteration every thread handles "quads" of 4 data: one Philox4x32-10 call gives
-//     the 4 uniforms, the K logits  c_k - a_k*tick  live in registers, max-subtracted
-//     exp2 (MUFU.EX2), sequential cumulative sum, inverse-CDF label
-//     (gibbs.py:196-200);
+//     the 4 uniforms; a quad inside the window finds its labels by a binary search directly
+//     on the rows (two quads in flight per thread), any other quad recomputes its row in
+//     registers with the same arithmetic (MUFU.EX2; the oracle's max-subtracted IEEE-only
+//     form in EXACT mode); inverse-CDF label either way (gibbs.py:196-200);
 //   * sufficient statistics (n_k, sum of ticks) are exact integers (gibbs.py:203-207):
 //     shared-memory atomics for every label except the currently dominant one, whose
 //     statistics follow by subtraction from the slice totals;
 //   * team members post their partials into the chain's tagged mailboxes in L2 (one
 //     64-bit word per value, valid once it carries the iteration number -- no fence, no
 //     flag) and every warp gathers a share of them; teams wider than 32 CTAs fall back to
-//     L2 atomics + a monotonic arrive counter.  Every member then draws the same
-//     Dirichlet / Gamma update (gibbs.py:210-211) from the same Philox key (lane k =
-//     component k, one Marsaglia-Tsang trial per warp in parallel), so no broadcast is needed;
-//   * every `thin`-th iteration the labels (4 per 32-bit store) and, from team rank 0,
-//     the post-update weights/rates are written (gibbs.py:214-217).
+//     L2 atomics + a monotonic arrive counter; one chain sharded over several GPUs adds a
+//     second level over NVLink.  Every member then draws the same Dirichlet / Gamma update
+//     (gibbs.py:210-211) from the same Philox key (lane k = component k, one Marsaglia-Tsang
+//     trial per warp in parallel), so no broadcast is needed;
+//   * every `thin`-th iteration the labels and, from team rank 0, the post-update
+//     weights/rates are written (gibbs.py:214-217).
 //
-// No tensor cores: nothing here is a contraction.  The roofline is the MUFU (XU) pipe:
-// one ex2 per (datum, component) pair.
+// Everything random is keyed by (chain, iteration, datum or component) and every statistic is an
+// integer, so the result does not depend on the schedule: any team size, slicing, wave order or
+// number of GPUs gives the same bits.
+//
+// No tensor cores: nothing here is a contraction.  The stated roofline is the MUFU (XU) pipe, one
+// ex2 per (datum, component) pair; with the memoised rows the kernel is issue/latency-bound.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -679,7 +688,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
         const float* const inj_u_base = inject_u ? b.inj_u + b.inj_u_offset[r] : nullptr;
         const size_t u_pitch = (size_t)((n_data + 3) / 4) * 4;
 
-        // ---- stage the slice: integer ticks -> float32 in shared memory -----------------
+        // ---- stage the slice: integer ticks into shared memory, slice totals, tick range ----
         unsigned my_n = 0, my_lo = 0xffffffffu, my_hi = 0u;
         unsigned long long my_t = 0;
         for (int q = tid; q < nq; q += THREADS) {
