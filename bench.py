@@ -214,7 +214,6 @@ def run_b200_arm(args):
 
     import torch
     import torch.distributed as dist
-    from basicrta_b200 import _cabi
     from basicrta_b200.engine import ChainInput, GibbsEngine
     from basicrta_b200.plan import shard_chains
 

@@ -7,7 +7,6 @@ import json
 import os
 import sys
 
-import numpy as np
 
 sys.path.insert(0, '.')
 import torch  # noqa: E402
