@@ -14,7 +14,7 @@ SRC = os.path.join(HERE, 'csrc', 'brta_gibbs.cu')
 SRC_PINDICATOR = os.path.join(HERE, 'csrc', 'brta_pindicator.cu')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 THREADS = 128
 MAX_NCOMP = 32
 TICK_LIMIT = 1 << 23
@@ -81,6 +81,7 @@ class Batch(C.Structure):
         ('shard_totals', C.c_void_p),
         ('exchange', C.c_void_p), ('exch_offset', C.c_void_p),
         ('task_cycles', C.c_void_p),
+        ('iter_begin', C.c_int32), ('iter_end', C.c_int32), ('final_c', C.c_void_p), ('final_a', C.c_void_p),
     ]
 
 

@@ -662,6 +662,8 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
     const int niter = b.niter;
     const int thin = b.thin;
     const int rows = (niter + 1) / thin;
+    const int j_begin = b.iter_begin;                        // this launch runs iterations j_begin + 1 .. j_end
+    const int j_end = b.iter_end > 0 ? b.iter_end : niter;
     const bool inject_coef = (b.flags & BRTA_FLAG_INJECT_COEF) != 0;
     const bool inject_u = (b.flags & BRTA_FLAG_INJECT_U) != 0;
     const bool trace = (b.flags & BRTA_FLAG_TRACE) != 0;
@@ -770,7 +772,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
         bool bad = false;
         unsigned long long busy_cycles = 0;                // schedule feedback: iteration start -> post
         PHASE_DECL
-        for (int j = 1; j <= niter; ++j) {
+        for (int j = j_begin + 1; j <= j_end; ++j) {
             const long long iter_t0 = b.task_cycles ? clock64() : 0;
             if (inject_coef) {
                 if (tid < kreal) {
@@ -804,7 +806,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
             PHASE_MARK(0);                                 // sweep
             __syncthreads();
             PHASE_MARK(1);                                 // wait for the CTA's slowest warp
-            if (b.task_cycles && 2 * j > niter) busy_cycles += (unsigned long long)(clock64() - iter_t0);
+            if (b.task_cycles && 2 * (j - j_begin) > j_end - j_begin) busy_cycles += (unsigned long long)(clock64() - iter_t0);
 
             // ---- this CTA's partials; the uncounted dominant label follows by subtraction --
             if (warp == lead) {
@@ -836,7 +838,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
                         __threadfence();
                         atomicAdd(ex_arrive, 1u);
                     }
-                    const unsigned target = (unsigned)team * (unsigned)j;
+                    const unsigned target = (unsigned)team * (unsigned)(j - j_begin);   // the counter starts at 0 every launch
                     unsigned spins = 0;
                     while (ld_acquire_u32(ex_arrive) < target) {
                         if (++spins > SPIN_LIMIT) { s_abort = 1u; break; }
@@ -1037,6 +1039,10 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
         }
         PHASE_FLUSH;
         if (b.task_cycles && tid == 0) b.task_cycles[ti] = busy_cycles;
+        if (b.final_c && b.final_a && task.team_rank == 0 && tid < kreal) {   // state for a following launch
+            b.final_c[(size_t)r * kreal + tid] = s_coef[tid].x;
+            b.final_a[(size_t)r * kreal + tid] = s_coef[tid].y;
+        }
         if (bad) atomicOr(&s_bad, 1u);
         __syncthreads();
         if (tid == 0 && s_bad) atomicOr(reinterpret_cast<unsigned*>(&b.status[r]), (unsigned)BRTA_STATUS_NONFINITE);
@@ -1170,6 +1176,9 @@ int brta_gibbs_run_batch(const brta_batch* batch, void* stream)
     if (b.ncomp < 1 || !v) return brta::fail(BRTA_E_NCOMP, "ncomp must be in 1..32");
     if (b.n_chains < 1 || b.niter < 1 || b.thin < 1 || b.grid_ctas < 1 || b.slice_cap_quads < 1)
         return brta::fail(BRTA_E_RANGE, "n_chains, niter, thin, grid_ctas, slice_cap_quads must be >= 1");
+    if (b.iter_begin < 0 || b.iter_end < 0 || b.iter_end > b.niter ||
+        b.iter_begin >= (b.iter_end > 0 ? b.iter_end : b.niter))
+        return brta::fail(BRTA_E_RANGE, "0 <= iter_begin < iter_end <= niter required (iter_end = 0: niter)");
     if (b.tick_bytes != 2 && b.tick_bytes != 4)
         return brta::fail(BRTA_E_RANGE, "tick_bytes must be 2 or 4");
     if (!b.max_tick) return brta::fail(BRTA_E_NULL, "max_tick is required");

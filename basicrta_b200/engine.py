@@ -111,11 +111,17 @@ class DeviceBatch:
     h2d_bytes: int = 0
     units: float = 0.0                                # sum_r N_r * K * niter
     executed_ex2_share: float = 1.0                   # ex2 actually executed / units (memoised rows make it < 1)
+    segments: list = None                              # iteration ends of the launches of one run (None: one launch)
+    cal: tuple = None                                  # (costs, ticks, tick_offset) for re-slicing between segments
 
 
 CALIBRATE_MIN_NITER = 2000     # shorter runs are not worth the calibration launches
 CALIBRATE_ITERS = 96           # iterations per calibration launch (the kernel times the second half)
 CALIBRATE_ROUNDS = 2
+SEGMENT_MIN_NITER = 20000      # longer calibrated runs are cut into launches and re-sliced in between
+SEGMENT_FRACTIONS = (0.02, 0.06, 0.15, 0.3, 0.5, 0.75)
+SEGMENT_DAMPING = 0.5          # move the boundaries half of the way to the measured optimum (noise, one-segment lag)
+SEGMENT_MIN_SPREAD = 0.15      # teams whose members are within 15 % of each other are left alone
 
 
 class GibbsEngine:
@@ -162,7 +168,7 @@ class GibbsEngine:
         # dynamic shared memory in 16-byte units: the largest task slice
         units = np.where(narrow[plan.tasks['chain']], (plan.tasks['quad_count'] + 1) // 2, plan.tasks['quad_count'])
         plan.smem_units = int(units.max())
-        plan.cap_quads, plan.cap_units = cap, int(cap16)
+        plan.cap_quads, plan.cap_units, plan.tick_total = cap, int(cap16), {}
         check = _cabi.launch_info(self.device, ncomp, flags, plan.smem_units)
         if check.ctas_per_sm < per_sm:
             raise _cabi.BrtaError('schedule assumes more co-resident CTAs than the device grants')
@@ -170,7 +176,7 @@ class GibbsEngine:
 
     # ---- pack + upload -------------------------------------------------------------------
     def prepare(self, chains, ncomp, niter, thin=100, seed=0, flags=0, inject=None, n_waves=None, shard=None,
-                calibrate=None):
+                calibrate=None, segments=None):
         """``chains``: list of :class:`ChainInput`.  ``inject``: dict with optional
         ``coef_c``/``coef_a`` (list of [niter,K] float32) and ``u`` (list of [niter,N]).
         ``shard`` (internal, see :func:`run_sharded`): this GPU's part of ONE chain split over
@@ -339,6 +345,19 @@ class GibbsEngine:
         if calibrate:
             if shard is not None or flags & (_cabi.FLAG_INJECT_COEF | _cabi.FLAG_INJECT_U | _cabi.FLAG_TRACE):
                 raise ValueError('calibration needs a plain (not sharded, not injected, not traced) batch')
+            # every launch ends with a tail in which CTAs run dry; with several waves that tail is long (the
+            # waves are only balanced over the whole run), so only single-wave schedules are segmented by default
+            if segments is None and niter >= SEGMENT_MIN_NITER and plan.n_waves == 1:
+                segments = SEGMENT_FRACTIONS
+            if segments:
+                ends = sorted({int(round(f * niter / thin)) * int(thin) for f in segments} | {int(niter)})
+                ends = [e for e in ends if 0 < e <= niter]
+                if len(ends) > 2:
+                    for name in ('c', 'a'):
+                        T['final_' + name] = torch.zeros((R, K), dtype=torch.float32, device=dev)
+                        T['init_' + name + '0'] = T['init_' + name].clone()
+                    b.final_c, b.final_a = T['final_c'].data_ptr(), T['final_a'].data_ptr()
+                    db.segments, db.cal = ends, (costs, ticks, tick_offset)
             for _ in range(CALIBRATE_ROUNDS):
                 self._calibrate(db, costs, ticks, tick_offset)
         if shard is None and costs is not None:
@@ -381,6 +400,52 @@ class GibbsEngine:
         self.reset(db)
         return times
 
+    @staticmethod
+    def _rebalanced(plan, tasks, times, costs, ticks, tick_offset, damping=1.0, min_spread=0.0):
+        """Host side of the measured slicing: a copy of ``tasks`` whose slice boundaries inside every team
+        cut the measured time density (``times[i]`` = cycles of task i) into equal parts (or move
+        ``damping`` of the way there), and the dynamic shared memory (16-byte units) the new slices need."""
+        tasks = tasks.copy()
+        narrow = plan.cap_quads > plan.cap_units                    # chains at 8 B per quad
+        by_chain = [[] for _ in range(len(plan.team_size))]
+        for i, c in enumerate(tasks['chain']):
+            by_chain[int(c)].append(i)
+        for r, idx in enumerate(by_chain):
+            if len(idx) < 2:
+                continue
+            idx.sort(key=lambda i: int(tasks[i]['team_rank']))
+            t_team = times[idx]
+            if min_spread > 0.0 and np.ptp(t_team) < min_spread * t_team.mean():
+                continue                                           # balanced well enough: leave it alone
+            last = tasks[idx[-1]]
+            bounds = np.array([int(tasks[i]['quad_begin']) for i in idx] + [int(last['quad_begin'] + last['quad_count'])])
+            weight = None
+            if costs is not None:
+                weight = np.full(int(bounds[-1]), COST_DIRECT)
+                for k in range(len(idx)):
+                    s0, e0 = int(bounds[k]), int(bounds[k + 1])
+                    weight[s0:s0 + costs[r].served(s0, e0)] = COST_SERVED
+            new = rebalance_team(bounds, np.maximum(times[idx], 1.0), weight, cap=int(plan.cap_quads[r]))
+            if damping < 1.0:                                      # move only part of the way (noisy measurements)
+                new = np.rint(bounds + damping * (new - bounds)).astype(np.int64)
+                if np.any(np.diff(new) < 1):
+                    continue
+            # per-iteration slice sums are accumulated in 32 bits inside a CTA: nothing to check if the
+            # whole chain sums to less (cached), else every new slice
+            total = plan.tick_total.get(r)
+            if total is None:
+                total = plan.tick_total[r] = int(np.sum(ticks[tick_offset[r]:tick_offset[r] + 4 * int(bounds[-1])], dtype=np.int64))
+            if total >= (1 << 32):
+                cs = np.concatenate(([0], np.cumsum(ticks[tick_offset[r]:tick_offset[r] + 4 * int(bounds[-1])], dtype=np.int64)))
+                hi = np.minimum(4 * new[1:], len(cs) - 1)
+                if np.any(cs[hi] - cs[4 * new[:-1]] >= (1 << 32)):
+                    continue
+            for k, i in enumerate(idx):
+                tasks[i]['quad_begin'], tasks[i]['quad_count'] = int(new[k]), int(new[k + 1] - new[k])
+        units = np.where(narrow[tasks['chain']], (tasks['quad_count'] + 1) // 2, tasks['quad_count'])
+        assert int(units.max()) <= plan.cap_units
+        return tasks, int(units.max())
+
     def _calibrate(self, db, costs, ticks, tick_offset, iters=None):
         """Measured slicing.  The members of a team wait for the slowest one every iteration, and the
         time a slice takes depends on more than the cost model knows (memoised rows built, label mix
@@ -392,37 +457,10 @@ class GibbsEngine:
         torch = self.torch
         plan, T, H = db.plan, db.tensors, db.host
         times = self._measure(db, CALIBRATE_ITERS if iters is None else int(iters))
-        tasks = plan.tasks
-        narrow = plan.cap_quads > plan.cap_units                    # chains at 8 B per quad
-        by_chain = [[] for _ in range(len(plan.team_size))]
-        for i, t in enumerate(tasks):
-            by_chain[int(t['chain'])].append(i)
-        for r, idx in enumerate(by_chain):
-            if len(idx) < 2:
-                continue
-            idx.sort(key=lambda i: int(tasks[i]['team_rank']))
-            last = tasks[idx[-1]]
-            bounds = np.array([int(tasks[i]['quad_begin']) for i in idx] + [int(last['quad_begin'] + last['quad_count'])])
-            weight = None
-            if costs is not None:
-                weight = np.full(int(bounds[-1]), COST_DIRECT)
-                for k in range(len(idx)):
-                    s0, e0 = int(bounds[k]), int(bounds[k + 1])
-                    weight[s0:s0 + costs[r].served(s0, e0)] = COST_SERVED
-            new = rebalance_team(bounds, np.maximum(times[idx], 1.0), weight, cap=int(plan.cap_quads[r]))
-            # per-iteration slice sums are accumulated in 32 bits inside a CTA
-            cs = np.concatenate(([0], np.cumsum(ticks[tick_offset[r]:tick_offset[r] + 4 * int(bounds[-1])], dtype=np.int64)))
-            hi = np.minimum(4 * new[1:], len(cs) - 1)
-            if np.any(cs[hi] - cs[4 * new[:-1]] >= (1 << 32)):
-                continue
-            for k, i in enumerate(idx):
-                tasks[i]['quad_begin'], tasks[i]['quad_count'] = int(new[k]), int(new[k + 1] - new[k])
-        units = np.where(narrow[tasks['chain']], (tasks['quad_count'] + 1) // 2, tasks['quad_count'])
-        plan.smem_units = int(units.max())
-        plan.slice_cap_quads = int(tasks['quad_count'].max())
-        assert plan.smem_units <= plan.cap_units
+        plan.tasks, plan.smem_units = self._rebalanced(plan, plan.tasks, times, costs, ticks, tick_offset)
+        plan.slice_cap_quads = int(plan.tasks['quad_count'].max())
         db.batch.slice_cap_quads = plan.smem_units
-        H['tasks'].copy_(torch.from_numpy(np.ascontiguousarray(tasks.view(np.int32).reshape(-1, 6))))
+        H['tasks'].copy_(torch.from_numpy(np.ascontiguousarray(plan.tasks.view(np.int32).reshape(-1, 6))))
         T['tasks'].copy_(H['tasks'], non_blocking=True)
         torch.cuda.current_stream(T['tasks'].device).synchronize()
         return times
@@ -434,11 +472,85 @@ class GibbsEngine:
         db.tensors['status'].zero_()
 
     def launch(self, db, stream=None):
+        """Enqueue the whole run.  Long calibrated runs go as several back-to-back launches
+        (``db.segments``) so that the slicing can follow the slowly drifting cost of the slices; the
+        call then returns once the last segment is enqueued (it waits for the earlier ones)."""
         torch = self.torch
         with torch.cuda.device(self.device):
             s = torch.cuda.current_stream() if stream is None else stream
+            if db.segments and len(db.segments) > 2:
+                with torch.cuda.stream(s):
+                    self._launch_segmented(db, s)
+                return
             rc = self.lib.brta_gibbs_run_batch(C.byref(db.batch), C.c_void_p(s.cuda_stream))
         _cabi.check(rc, 'brta_gibbs_run_batch')
+
+    def _side_stream(self):
+        if getattr(self, '_side', None) is None:
+            with self.torch.cuda.device(self.device):
+                self._side = self.torch.cuda.Stream()
+        return self._side
+
+    def _launch_segmented(self, db, s):
+        """Launch k runs iterations ends[k-1]+1 .. ends[k] from the state launch k-1 left in (final_c, final_a).
+        Launches 0 and 1 use the current slicing; launch k >= 2 uses a slicing re-cut from the task cycles
+        of launch k-2, computed on the host while launch k-1 runs (two task buffers, two cycle buffers), so
+        the GPU never waits for the host.  Philox counters, row indices and integer statistics are those of
+        the single launch: same bits."""
+        torch = self.torch
+        T, plan = db.tensors, db.plan
+        costs, ticks, tick_offset = db.cal
+        ends = db.segments
+        dev = T['tasks'].device
+        n_tasks = len(plan.tasks)
+        if 'tasks_b' not in T or T['tasks_b'].shape != T['tasks'].shape:
+            T['tasks_b'] = torch.empty_like(T['tasks'])
+            T['cycles'] = torch.zeros((2, n_tasks), dtype=torch.int64, device=dev)
+        T['init_c'].copy_(T['init_c0'])
+        T['init_a'].copy_(T['init_a0'])
+        bufs = (T['tasks'], T['tasks_b'])
+        used = [None] * len(ends)                      # (host tasks, smem units) each launch ran with
+        events = []
+        cur = (plan.tasks, plan.smem_units)
+        begin = 0
+        for k, end in enumerate(ends):
+            which = 0 if k < 2 else (k & 1) ^ 1        # launches 0, 1: buffer 0; then the buffer launch k-2 used
+            if k >= 2:
+                events[k - 2].synchronize()
+                with torch.cuda.stream(self._side_stream()):        # launch k-1 is running on s: stay off it
+                    times = T['cycles'][k & 1].cpu().numpy().astype(np.float64)
+                    cur = self._rebalanced(plan, used[k - 2][0], times, costs, ticks, tick_offset, SEGMENT_DAMPING, SEGMENT_MIN_SPREAD)
+                    bufs[which].copy_(torch.from_numpy(np.ascontiguousarray(cur[0].view(np.int32).reshape(-1, 6))))
+                    ready = torch.cuda.Event()
+                    ready.record()
+                s.wait_event(ready)
+            elif k == 0:
+                bufs[0].copy_(torch.from_numpy(np.ascontiguousarray(cur[0].view(np.int32).reshape(-1, 6))))
+            used[k] = cur
+            if k > 0:
+                T['init_c'].copy_(T['final_c'])
+                T['init_a'].copy_(T['final_a'])
+                T['exchange'].zero_()
+            T['cycles'][k & 1].zero_()
+            seg = _cabi.Batch.from_buffer_copy(db.batch)
+            seg.iter_begin, seg.iter_end = int(begin), int(end)
+            seg.tasks = bufs[which].data_ptr()
+            seg.slice_cap_quads = int(cur[1])
+            seg.task_cycles = T['cycles'][k & 1].data_ptr()
+            rc = self.lib.brta_gibbs_run_batch(C.byref(seg), C.c_void_p(s.cuda_stream))
+            _cabi.check(rc, 'brta_gibbs_run_batch (segment)')
+            ev = torch.cuda.Event()
+            ev.record(s)
+            events.append(ev)
+            begin = end
+        # keep the latest slicing for the next run of this batch
+        plan.tasks, plan.smem_units = cur
+        plan.slice_cap_quads = int(plan.tasks['quad_count'].max())
+        db.batch.slice_cap_quads = plan.smem_units
+        db.host['tasks'].copy_(torch.from_numpy(np.ascontiguousarray(plan.tasks.view(np.int32).reshape(-1, 6))))
+        if bufs[which] is not T['tasks']:
+            T['tasks'], T['tasks_b'] = T['tasks_b'], T['tasks']
+            db.batch.tasks = T['tasks'].data_ptr()
 
     # ---- host <-> device legs, separately callable so they can be timed / overlapped -------
     def upload(self, db):

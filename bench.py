@@ -317,13 +317,14 @@ def run_b200_arm(args):
                                    f'ncomp={NCOMP}, niter={niter}, thin={THIN}; residues sharded over {world} GPU(s), '
                                    f'no collective',
                        'l2': 'flushed between steps (256 MiB write); chain data lives in shared memory',
-                       'launch': f'1 persistent cooperative launch per step per GPU, grid {db.plan.grid} x 128 threads, '
+                       'launch': f'{len(db.segments) if db.segments and len(db.segments) > 2 else 1} back-to-back persistent cooperative launch(es) per step per GPU '
+                                 f'(slices re-cut in between from measured cycles), grid {db.plan.grid} x 128 threads, '
                                  f'{db.plan.n_waves} waves, teams {int(db.plan.team_size.min())}-{int(db.plan.team_size.max())} CTAs'},
             'residues_per_hour': n_res * 3600.0 / sec,
             'e2e': {'value': total_units / (e2e_ms * 1e-3 / args.steps), 'unit': UNIT,
                     'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes,
                     'ms_per_step': e2e_ms / args.steps},
-            'gpu_launches': args.steps * world,
+            'gpu_launches': args.steps * world * (len(db.segments) if db.segments and len(db.segments) > 2 else 1),
             'per_rank_ms_per_step': [round(x, 3) for x in per_rank_ms],
             'roofline': {'bound': 'mufu', 'achieved': per_gpu / 1e9, 'peak': peak / 1e9, 'unit': 'G ex2/s',
                          'frac': per_gpu / peak, 'traffic': profiled_traffic(n_res, niter, world),

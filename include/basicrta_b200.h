@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BRTA_ABI_VERSION 2
+#define BRTA_ABI_VERSION 3
 
 /* compile-time geometry of the sampler kernel */
 #ifndef BRTA_THREADS
@@ -182,10 +182,20 @@ typedef struct brta_batch {
     const int64_t*   exch_offset;  /* [R] byte offsets, multiples of 128                 */
 
     /* schedule feedback (may be NULL): task i gets the clock cycles its CTA spent from the start of an
-     * iteration to the post of its partial statistics, summed over the second half of the iterations
+     * iteration to the post of its partial statistics, summed over the second half of the launch's iterations
      * (the first ones start from the initial state and are not typical).  A short launch
      * with this set tells the scheduler how long each slice really takes (see engine.calibrate). */
     uint64_t*        task_cycles;  /* [number of tasks]                                  */
+
+    /* one chain run as several consecutive launches (so that the schedule can be re-cut in between):
+     * this launch runs iterations iter_begin + 1 .. iter_end of the niter (iter_end = 0 means niter),
+     * starting from (init_c, init_a); iteration numbers, Philox counters and row indices stay those of
+     * the whole run, so any segmentation gives the bits of a single launch.  The exchange workspace
+     * must be zeroed before every launch. */
+    int32_t          iter_begin;   /* iterations already done, 0 <= iter_begin < iter_end */
+    int32_t          iter_end;     /* last iteration of this launch, <= niter; 0 = niter  */
+    float*           final_c;      /* [R,K] may be NULL: coefficients after iteration iter_end, */
+    float*           final_a;      /* [R,K] the (init_c, init_a) of the next launch             */
 } brta_batch;
 
 /* Device capabilities.  Python side: Gibbs.run needs it to size the schedule. */

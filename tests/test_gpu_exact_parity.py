@@ -113,6 +113,34 @@ def test_measured_slicing_changes_the_schedule_not_the_results(engine):
         np.testing.assert_array_equal(a.indicator, b.indicator)
 
 
+def test_segmented_run_is_bit_identical_to_one_launch(engine):
+    """Long calibrated runs go as several back-to-back launches (iter_begin / iter_end, state handed over in
+    final_c / final_a) with the slices re-cut in between from measured cycles.  Iteration numbers, Philox
+    counters and row indices are those of the whole run: same bits as a single launch, also when the same
+    batch is launched a second time."""
+    rng = np.random.default_rng(21)
+    chains = []
+    for r, n in enumerate((26000, 7001, 41000, 900, 15000)):
+        comp = rng.choice(3, size=n, p=[0.7, 0.2, 0.1])
+        x = rng.exponential(1.0 / np.array([3.0, 0.2, 0.004])[comp])
+        chains.append(ChainInput(ticks=np.maximum(np.ceil(x / 0.1), 1).astype(np.int64), ts=0.1, chain_id=70 + r))
+    K, niter, thin = 15, 600, 20
+    one = engine.prepare(chains, K, niter, thin=thin, seed=9, calibrate=False)
+    engine.launch(one)
+    ref = engine.fetch(one)
+    cut = engine.prepare(chains, K, niter, thin=thin, seed=9, calibrate=True, segments=(0.1, 0.2, 0.45, 0.7, 0.9))
+    assert cut.segments == [60, 120, 280, 420, 540, 600]
+    for _ in range(2):
+        engine.reset(cut)
+        engine.launch(cut)
+        got = engine.fetch(cut)
+        for a, b in zip(ref, got):
+            assert b.status == 0
+            np.testing.assert_array_equal(a.mcweights, b.mcweights)
+            np.testing.assert_array_equal(a.mcrates, b.mcrates)
+            np.testing.assert_array_equal(a.indicator, b.indicator)
+
+
 def test_fast_mode_flip_rate(engine):
     """FAST (MUFU.EX2 + FMA contraction) differs from EXACT only where a uniform lands within
     float rounding of a CDF boundary: < 1e-4 of the labels, and the statistics stay close."""
