@@ -103,3 +103,40 @@ def test_shard_chains_lpt():
     loads = [costs[s].sum() for s in shards]
     assert max(loads) - min(loads) <= 20
     assert all(len(s) == 0 for s in shard_chains([], 2))
+
+
+def test_engine_rebalance_host_logic():
+    """GibbsEngine._rebalanced (pure NumPy): slices of a team follow the measured task cycles, optionally
+    damped; balanced teams and single-CTA chains are left alone; every chain stays tiled."""
+    from types import SimpleNamespace
+
+    from basicrta_b200.engine import GibbsEngine
+    from basicrta_b200.plan import TASK_DTYPE
+    # chain 0: 4 slices of 1000 quads, chain 1: one slice, chain 2: 2 slices
+    tasks = np.array([(0, 4, 0, 0, 1000, 0), (0, 4, 1, 1000, 1000, 0), (0, 4, 2, 2000, 1000, 0), (0, 4, 3, 3000, 1000, 0),
+                      (1, 1, 0, 0, 500, 0), (2, 2, 0, 0, 300, 0), (2, 2, 1, 300, 300, 0)], dtype=TASK_DTYPE)
+    plan = SimpleNamespace(team_size=np.array([4, 1, 2]), cap_quads=np.array([4000, 4000, 4000]), cap_units=2000,
+                           tick_total={})
+    ticks = np.ones(4 * (4000 + 500 + 600), dtype=np.uint16)
+    tick_offset = np.array([0, 16000, 18000])
+    times = np.array([1000.0, 1000.0, 2000.0, 4000.0, 700.0, 500.0, 520.0])
+
+    def tiles(t):
+        for r, nq in ((0, 4000), (1, 500), (2, 600)):
+            mine = np.sort(t[t['chain'] == r], order='team_rank')
+            assert mine['quad_begin'][0] == 0 and mine['quad_begin'][-1] + mine['quad_count'][-1] == nq
+            assert np.array_equal(mine['quad_begin'][1:], (mine['quad_begin'] + mine['quad_count'])[:-1])
+
+    full, units = GibbsEngine._rebalanced(plan, tasks, times, None, ticks, tick_offset)
+    tiles(full)
+    assert tasks['quad_count'][3] == 1000                                 # the input is not modified
+    c0 = full[full['chain'] == 0]['quad_count']
+    assert c0[3] < 600 and c0[0] > 1500 and units == (int(full['quad_count'].max()) + 1) // 2
+    half, _ = GibbsEngine._rebalanced(plan, tasks, times, None, ticks, tick_offset, damping=0.5)
+    tiles(half)
+    h0 = half[half['chain'] == 0]['quad_count']
+    assert c0[3] < h0[3] < 1000 and 1000 < h0[0] < c0[0]                  # half of the way
+    lazy, _ = GibbsEngine._rebalanced(plan, tasks, times, None, ticks, tick_offset, min_spread=0.15)
+    assert np.array_equal(lazy[lazy['chain'] == 2], tasks[tasks['chain'] == 2])   # 4 % spread: untouched
+    assert not np.array_equal(lazy[lazy['chain'] == 0], tasks[tasks['chain'] == 0])
+    assert np.array_equal(full[full['chain'] == 1], tasks[tasks['chain'] == 1])
