@@ -124,6 +124,15 @@ SEGMENT_DAMPING = 0.5          # move the boundaries half of the way to the meas
 SEGMENT_MIN_SPREAD = 0.15      # teams whose members are within 15 % of each other are left alone
 
 
+def _canonical_order(ticks):
+    """Stable ascending-tick order (oracle.gibbs_oracle.canonical_order).  16-bit keys take NumPy's radix
+    sort, 4x faster than the comparison sort of int64 -- the sort is the largest host cost of a batch."""
+    t = np.asarray(ticks)
+    if t.size and 0 <= int(t.min()) and int(t.max()) < 65536:
+        t = t.astype(np.uint16)
+    return np.argsort(t, kind='stable').astype(np.int32)
+
+
 class GibbsEngine:
     """One engine per GPU.  ``prepare`` (pack + H2D), ``launch`` (async kernel),
     ``fetch`` (D2H) are separate so callers can time and overlap them."""
@@ -204,7 +213,7 @@ class GibbsEngine:
         tick_dtype = np.uint16 if max_tick < 65536 else np.uint32
 
         # canonical order: ascending ticks (stable).  Philox word p belongs to canonical position p.
-        order = [np.argsort(np.asarray(ch.ticks), kind='stable').astype(np.int32) for ch in chains]
+        order = [_canonical_order(ch.ticks) for ch in chains]
         if shard is not None:
             if R != 1:
                 raise ValueError('a sharded launch holds exactly one chain')
