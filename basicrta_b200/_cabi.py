@@ -10,17 +10,17 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('BRTA_LIB', os.path.join(HERE, 'libbrta_gibbs.so'))   # BRTA_LIB: developer override
-SRC = os.path.join(HERE, 'csrc', 'brta_gibbs.cu')
-SRC_PINDICATOR = os.path.join(HERE, 'csrc', 'brta_pindicator.cu')
+CSRC = os.path.join(HERE, 'csrc')
+OBJ_DIR = os.path.join(CSRC, '_obj')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 THREADS = 128
 MAX_NCOMP = 32
 TICK_LIMIT = 1 << 23
 MAILBOX_MAX_TEAM = 32
 MAX_SHARDS = 16
-SHARD_TOTALS_BYTES = 3 * 32 * 16 + 128
+IPC_HANDLE_BYTES = 64
 
 
 def shard_mailbox_bytes(g):
@@ -78,35 +78,65 @@ class Batch(C.Structure):
         ('tasks', C.c_void_p), ('cta_task_begin', C.c_void_p), ('grid_ctas', C.c_int32),
         ('slice_cap_quads', C.c_int32),
         ('n_shards', C.c_int32), ('shard_rank', C.c_int32), ('shard_mailbox', C.c_void_p),
-        ('shard_totals', C.c_void_p),
         ('exchange', C.c_void_p), ('exch_offset', C.c_void_p),
         ('task_cycles', C.c_void_p),
         ('iter_begin', C.c_int32), ('iter_end', C.c_int32), ('final_c', C.c_void_p), ('final_a', C.c_void_p),
+        ('watchdog_ns', C.c_uint64), ('device', C.c_int32), ('reserved0', C.c_int32),
     ]
 
 
 EXPORTS = ('brta_abi_version', 'brta_last_error', 'brta_query', 'brta_gibbs_launch_info',
            'brta_gibbs_run_batch', 'brta_philox_fill', 'brta_mufu_probe', 'brta_enable_peer_access',
-           'brta_pindicator_counts')
+           'brta_pindicator_counts', 'brta_gamma_fill', 'brta_shard_mailbox_create', 'brta_shard_mailbox_open',
+           'brta_shard_mailbox_close', 'brta_shard_mailbox_destroy', 'brta_shard_mailbox_clear')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '-shared', '-Xcompiler', '-fPIC']
+              '-Xcompiler', '-fPIC']
+SWEEP_NCOMPS = (2, 3, 4, 5, 6, 8, 10, 12, 15, 16, 20, 24, 30, 32)      # BRTA_FOR_EACH_K of csrc/brta_gibbs.cu
+HEADERS = [os.path.join(CSRC, f) for f in ('brta_sweep.cuh', 'brta_math.cuh', 'brta_rng.cuh', 'brta_host.h')] + \
+          [os.path.join(INCLUDE, 'basicrta_b200.h')]
 
 
-def build(force=False, verbose=False):
-    """Compile ``csrc/brta_gibbs.cu`` for sm_100a into ``libbrta_gibbs.so`` (in-tree)."""
-    srcs = [SRC, SRC_PINDICATOR] + [os.path.join(HERE, 'csrc', f) for f in ('brta_math.cuh', 'brta_rng.cuh', 'brta_host.h')] + \
-           [os.path.join(INCLUDE, 'basicrta_b200.h')]
-    if (not force and os.path.exists(LIB_PATH) and
-            all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
-        return LIB_PATH
-    cmd = ['nvcc'] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH, SRC, SRC_PINDICATOR]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+def _newer(target, deps):
+    return os.path.exists(target) and all(os.path.getmtime(target) >= os.path.getmtime(d) for d in deps)
+
+
+def build(force=False, verbose=False, extra_flags=(), lib_path=None, ncomps=SWEEP_NCOMPS, jobs=None):
+    """Compile the library for sm_100a into ``libbrta_gibbs.so`` (in-tree): the host side
+    (``brta_gibbs.cu``), ``brta_pindicator.cu`` and one instantiation unit of the sweep kernel per
+    supported K (``brta_sweep_inst.cu -DBRTA_INST_K=k``), the units in parallel."""
+    from concurrent.futures import ThreadPoolExecutor
+    lib_path = lib_path or LIB_PATH
+    tag = ('_' + str(abs(hash(tuple(extra_flags))) % 10 ** 8)) if extra_flags else ''
+    units = [('host' + tag, os.path.join(CSRC, 'brta_gibbs.cu'), []),
+             ('pindicator' + tag, os.path.join(CSRC, 'brta_pindicator.cu'), [])]
+    units += [(f'sweep_k{k}' + tag, os.path.join(CSRC, 'brta_sweep_inst.cu'), [f'-DBRTA_INST_K={k}']) for k in ncomps]
+    objs = [os.path.join(OBJ_DIR, name + '.o') for name, _, _ in units]
+    if not force and _newer(lib_path, HEADERS + [u[1] for u in units]):
+        return lib_path
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    flags = NVCC_FLAGS + list(extra_flags) + (['-Xptxas', '-v'] if verbose else [])
+    if tuple(ncomps) != SWEEP_NCOMPS:
+        flags = flags + ['-DBRTA_ONLY_K15']
+
+    def compile_unit(unit_obj):
+        (name, src, defs), obj = unit_obj
+        if not force and _newer(obj, HEADERS + [src]):
+            return ''
+        res = subprocess.run(['nvcc'] + flags + defs + ['-c', '-o', obj, src], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise BrtaError(f'nvcc failed on {name}:\n' + res.stdout + res.stderr)
+        return res.stderr
+
+    with ThreadPoolExecutor(max_workers=jobs or min(len(units), os.cpu_count() or 1)) as pool:
+        logs = list(pool.map(compile_unit, zip(units, objs)))
+    res = subprocess.run(['nvcc', '-shared', '-o', lib_path] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a'],
+                         capture_output=True, text=True)
     if res.returncode != 0:
-        raise BrtaError('nvcc failed:\n' + res.stdout + res.stderr)
+        raise BrtaError('nvcc link failed:\n' + res.stdout + res.stderr)
     if verbose:
-        print(res.stderr)
-    return LIB_PATH
+        print('\n'.join(l for l in logs if l))
+    return lib_path
 
 
 _lib = None
@@ -132,6 +162,13 @@ def load():
     lib.brta_mufu_probe.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.brta_pindicator_counts.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                            C.c_int32, C.c_void_p, C.c_void_p]
+    lib.brta_gamma_fill.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint64,
+                                    C.c_void_p]
+    lib.brta_shard_mailbox_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_char_p]
+    lib.brta_shard_mailbox_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.brta_shard_mailbox_close.argtypes = [C.c_int, C.c_void_p]
+    lib.brta_shard_mailbox_clear.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    lib.brta_shard_mailbox_destroy.argtypes = [C.c_int, C.c_void_p]
     for name in EXPORTS:
         getattr(lib, name)
     if lib.brta_abi_version() != ABI_VERSION:

@@ -1,39 +1,6 @@
-// B200 (sm_100a) Gibbs sweep for basicrta's exponential-mixture residence-time model.
-//
-// Replaces the loop body of basicrta/gibbs.py:191-217 (reference: NumPy, one process per
-// residue) by ONE persistent cooperative launch per batch of residues:
-//
-//   * a chain (residue) is owned by a *team* of CTAs chosen by the host schedule
-//     (basicrta_b200/plan.py); each CTA keeps its slice of the residence times in shared
-//     memory for the whole run, as the integer ticks they are (times are integer multiples
-//     of ts, basicrta/contacts.py:222-229): 2 B per datum if the chain's ticks fit 16 bits;
-//   * the host passes a chain in ascending-tick order (labels go back through `perm`).  Once
-//     per iteration the CTA builds the K cumulative sums  sum_{k'<=k} 2^(c_k' - a_k' tick)
-//     for every tick value of a window of its slice ("memoised rows", shared memory);
-//   * per iteration every thread handles "quads" of 4 data: one Philox4x32-10 call gives
-//     the 4 uniforms; a quad inside the window finds its labels by a binary search directly
-//     on the rows (two quads in flight per thread), any other quad recomputes its row in
-//     registers with the same arithmetic (MUFU.EX2; the oracle's max-subtracted IEEE-only
-//     form in EXACT mode); inverse-CDF label either way (gibbs.py:196-200);
-//   * sufficient statistics (n_k, sum of ticks) are exact integers (gibbs.py:203-207):
-//     shared-memory atomics for every label except the currently dominant one, whose
-//     statistics follow by subtraction from the slice totals;
-//   * team members post their partials into the chain's tagged mailboxes in L2 (one
-//     64-bit word per value, valid once it carries the iteration number -- no fence, no
-//     flag) and every warp gathers a share of them; teams wider than 32 CTAs fall back to
-//     L2 atomics + a monotonic arrive counter; one chain sharded over several GPUs adds a
-//     second level over NVLink.  Every member then draws the same Dirichlet / Gamma update
-//     (gibbs.py:210-211) from the same Philox key (lane k = component k, one Marsaglia-Tsang
-//     trial per warp in parallel), so no broadcast is needed;
-//   * every `thin`-th iteration the labels and, from team rank 0, the post-update
-//     weights/rates are written (gibbs.py:214-217).
-//
-// Everything random is keyed by (chain, iteration, datum or component) and every statistic is an
-// integer, so the result does not depend on the schedule: any team size, slicing, wave order or
-// number of GPUs gives the same bits.
-//
-// No tensor cores: nothing here is a contraction.  The stated roofline is the MUFU (XU) pipe, one
-// ex2 per (datum, component) pair; with the memoised rows the kernel is issue/latency-bound.
+// Host side of libbrta_gibbs.so: the C ABI of include/basicrta_b200.h (argument checks, launches) and the
+// small auxiliary kernels.  The sweep kernel itself lives in brta_sweep.cuh and is instantiated once per
+// supported K by brta_sweep_inst.cu.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -41,1015 +8,9 @@
 
 #include "../../include/basicrta_b200.h"
 #include "brta_host.h"
-#include "brta_math.cuh"
-#include "brta_rng.cuh"
+#include "brta_sweep.cuh"
 
 namespace brta {
-
-constexpr int THREADS = BRTA_THREADS;
-constexpr int WARPS = THREADS / 32;
-constexpr unsigned SPIN_LIMIT = 1u << 25;                 // ~30 s of 1 us polls
-constexpr int NTRIALS = WARPS / 2;                        // Marsaglia-Tsang trials run in parallel per draw
-
-// exchange workspace of one chain (BRTA_EXCH_STRIDE bytes):
-//   sum[3][32] u64 @ 0, cnt[3][32] u32 @ 768, arrive u32 @ 1152
-constexpr int EXCH_SUM_OFF = 0;
-constexpr int EXCH_CNT_OFF = 768;
-constexpr int EXCH_ARRIVE_OFF = 1152;
-static_assert(EXCH_ARRIVE_OFF + 4 <= BRTA_EXCH_BYTES(BRTA_MAILBOX_MAX_TEAM + 1), "exchange layout");
-static_assert(WARPS >= 2, "the posterior update uses two warps");
-
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p)
-{
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p)
-{
-    unsigned v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ ulonglong2 ld_relaxed_v2(const ulonglong2* p)
-{
-    ulonglong2 v;
-    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_v2(ulonglong2* p, unsigned long long a, unsigned long long b)
-{
-    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" :: "l"(p), "l"(a), "l"(b) : "memory");
-}
-// system scope: words exchanged between GPUs over NVLink (peer-mapped memory)
-__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p)
-{
-    unsigned long long v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v)
-{
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v)
-{
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p)
-{
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-// Branch-free binary search in a sorted register array: the number of k with cum[k] <= thr.
-// cum is non-decreasing (sums of non-negative terms), so this equals the linear count the
-// oracle performs.  Level l compares against one pivot chosen from 2^(l-1) candidates by
-// the earlier predicates; the latest predicate drives the outermost select so only one
-// FSEL sits behind each FSETP.  K compares + K adds become ~log2(K) compares + K selects.
-template <int K, int P, int NB, int OFF, int STR>
-__device__ __forceinline__ float pivot_mux(const float (&cum)[K], const bool (&p)[5])
-{
-    if constexpr (NB == 0) {
-        if constexpr (OFF < P) return cum[OFF]; else return INFINITY;
-    } else {
-        const float hi = pivot_mux<K, P, NB - 1, OFF + STR, 2 * STR>(cum, p);
-        const float lo = pivot_mux<K, P, NB - 1, OFF, 2 * STR>(cum, p);
-        return p[NB - 1] ? hi : lo;
-    }
-}
-
-// level LVL of LEVELS: candidate j (bits p[0..LVL-2], p[0] most significant) sits at
-// index (2j+1) * 2^(LEVELS-LVL) - 1.
-template <int K, int P, int LEVELS, int LVL>
-__device__ __forceinline__ void search_level(const float (&cum)[K], float thr, bool (&p)[5], int& c)
-{
-    if constexpr (LVL <= LEVELS) {
-        const float pv = pivot_mux<K, P, LVL - 1, (1 << (LEVELS - LVL)) - 1, 1 << (LEVELS - LVL + 1)>(cum, p);
-        p[LVL - 1] = pv <= thr;
-        if (p[LVL - 1]) c |= (1 << (LEVELS - LVL));
-        search_level<K, P, LEVELS, LVL + 1>(cum, thr, p, c);
-    }
-}
-
-template <int K>
-__device__ __forceinline__ int count_le(const float (&cum)[K], float thr)
-{
-    // tree over the first P = 2^LEVELS - 1 (padded with +inf) entries; a power-of-two K
-    // keeps its last entry out of the tree and tests it directly.
-    constexpr bool POW2 = (K & (K - 1)) == 0;
-    constexpr int P = POW2 ? K - 1 : K;
-    constexpr int LEVELS = (P >= 16) ? 5 : (P >= 8) ? 4 : (P >= 4) ? 3 : (P >= 2) ? 2 : (P >= 1) ? 1 : 0;
-    bool p[5] = {false, false, false, false, false};
-    int c = 0;
-    search_level<K, P, LEVELS, 1>(cum, thr, p, c);
-    if constexpr (POW2) c += (cum[K - 1] <= thr) ? 1 : 0;
-    return c;
-}
-
-// Label of ONE datum with the max-subtracted logits of the oracle: the EXACT arithmetic, and
-// the rarely-taken safe path of the FAST mode.
-template <int K, bool EXACT>
-__device__ __forceinline__ int draw_label_maxsub(float tick, float f12, const float2* __restrict__ s_coef, int kmax)
-{
-    float l[K];
-    float m = -INFINITY;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const float2 ca = s_coef[k];
-        l[k] = EXACT ? __fsub_rn(ca.x, __fmul_rn(ca.y, tick)) : fmaf(-ca.y, tick, ca.x);
-        m = fmaxf(m, l[k]);
-    }
-    float cum = 0.0f;
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        cum = EXACT ? __fadd_rn(cum, soft_exp2(__fsub_rn(l[k], m))) : cum + fast_exp2(l[k] - m);
-        l[k] = cum;
-    }
-    // u = f12 - 1 is exact, so fma(f12, total, -total) is u * total rounded once: the same bits as
-    // the oracle's float32 product
-    const float thr = __fmaf_rn(f12, cum, -cum);
-    return min(count_le<K>(l, thr), kmax);
-}
-
-template <int K>
-__device__ __noinline__ int draw_label_safe(float tick, float f12, const float2* __restrict__ s_coef, int kmax)
-{
-    return draw_label_maxsub<K, false>(tick, f12, s_coef, kmax);
-}
-
-// Labels of D data at once.  l[d][k] holds the logit, then the running cumulative sum.
-//
-// EXACT: the oracle's arithmetic (max-subtracted logits, IEEE-only operations).
-// FAST : no max subtraction.  logit_k = log2(w_k r_k) - r_k t log2(e) is bounded above by
-//        log2(max rate) (w <= 1, t >= 0), far from float32 overflow, so the only hazard is
-//        underflow of EVERY term of a datum -- a state in which the datum would be impossible
-//        under all components (it occurs, if at all, in the first burn-in sweeps).  That is
-//        caught by one compare on the total and redone with the max-subtracted form.  Dropping
-//        the max removes a subtract per (datum, component) pair and the max tree: 92 of the
-//        476 instructions of a quad at K = 15.  Terms keep full float32 relative precision;
-//        the label differs from EXACT only where u lands within rounding of a CDF boundary.
-template <int K, int D, bool EXACT>
-__device__ __forceinline__ unsigned draw_labels(const float (&tick)[D], const float (&f12)[D],
-                                                const float2* __restrict__ s_coef, int kmax,
-                                                int (&lab)[D])
-{
-    unsigned redo = 0u;                                    // bit d: datum d underflowed, caller redoes it
-    if constexpr (EXACT) {
-#pragma unroll
-        for (int d = 0; d < D; ++d) lab[d] = draw_label_maxsub<K, true>(tick[d], f12[d], s_coef, kmax);
-    } else {
-        float l[D][K];
-        float cum[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) cum[d] = 0.0f;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float2 ca = s_coef[k];                   // broadcast LDS
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-                cum[d] += fast_exp2(fmaf(-ca.y, tick[d], ca.x));
-                l[d][k] = cum[d];
-            }
-        }
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            const float thr = __fmaf_rn(f12[d], cum[d], -cum[d]);
-            lab[d] = min(count_le<K>(l[d], thr), kmax);
-            if (!(cum[d] > 8.0779357e-28f)) redo |= 1u << d;   // total < 2^-90 (or NaN): TOTAL_FLOOR
-        }
-    }
-    return redo;
-}
-
-// data of one quad processed together by a thread (register pressure vs ILP)
-#ifndef BRTA_D_SMALLK
-#define BRTA_D_SMALLK 4
-#endif
-__host__ __device__ constexpr int data_in_flight(int k) { return k <= 16 ? BRTA_D_SMALLK : 2; }
-
-// Kernel parameters: the caller's batch plus the Philox key schedule, both in the constant bank.
-struct SweepParams {
-    brta_batch b;
-    RoundKeys rk;
-};
-
-// Shared-memory reductions of one datum: n_k += 1 and, 128 bytes further, the tick
-// accumulator, addressed in the shared window.
-__device__ __forceinline__ void red_shared_stats(uint32_t cnt_addr, uint32_t tick_bits)
-{
-    asm volatile("red.shared.add.u32 [%0], 1;\n\t"
-                 "red.shared.add.u32 [%0+128], %1;"
-                 :: "r"(cnt_addr), "r"(tick_bits) : "memory");
-}
-
-// ---- memoised cumulative rows ---------------------------------------------------------------
-// The cumulative sums of a datum depend on its tick only, and residence times are small
-// integers with huge multiplicities (half of a typical slice holds fewer than a dozen distinct
-// ticks once the chain is in ascending-tick order).  Once per iteration the CTA therefore
-// computes the K cumulative sums for every tick value lo, lo+1, ... of its slice (up to
-// TABLE_FLOATS / KP rows) with exactly the per-datum arithmetic, and a quad whose ticks all fall
-// in that range reads its rows instead of recomputing them: the same bits, without the K
-// FFMA + MUFU + FADD per datum.  Quads beyond the table (the sparse tail) take the direct path.
-constexpr int TABLE_FLOATS = 4096;                          // 16 KB of shared memory per CTA
-__host__ __device__ constexpr int table_row_floats(int k) { return (k + 3) / 4 * 4; }
-// rows are laid out with an odd stride so that the same entry of neighbouring rows (what the lanes
-// of a warp read during the search) falls into different banks
-__host__ __device__ constexpr int table_row_stride(int k) { return table_row_floats(k) + 1; }
-
-struct TableView {
-    uint32_t addr;           // shared-window byte address of row 0; row r = cumulative sums of tick lo + r
-    uint32_t lo;             // first tick of the table
-    uint32_t limit;          // quads with every tick < limit are served from the table (0: no table)
-};
-
-// Shared-memory accesses of the hot loop by explicit 32-bit address.  The compiler otherwise
-// re-derives the shared-window base of every access from SR_CgaCtaId (an S2UR + uniform-datapath
-// chain ahead of each load / reduction: a sixth of the stall samples of the first memoised kernel);
-// the kernels read the base once, through opaque_u32, and keep it in a register.
-__device__ __forceinline__ uint32_t opaque_u32(uint32_t x)
-{
-    uint32_t y;
-    asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
-    return y;
-}
-template <int OFF>
-__device__ __forceinline__ float lds_f32(uint32_t addr)
-{
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
-    return v;
-}
-__device__ __forceinline__ uint2 lds_v2(uint32_t addr)
-{
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ uint4 lds_v4(uint32_t addr)
-{
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-// ticks of quad q of a staged slice: 8 B per quad (16-bit ticks) or 16 B
-template <bool T16>
-__device__ __forceinline__ uint4 lds_quad(uint32_t slice_addr, int q)
-{
-    if constexpr (T16) {
-        const uint2 raw = lds_v2(slice_addr + 8u * (uint32_t)q);
-        return make_uint4(raw.x & 0xffffu, raw.x >> 16, raw.y & 0xffffu, raw.y >> 16);
-    } else {
-        return lds_v4(slice_addr + 16u * (uint32_t)q);
-    }
-}
-
-template <int K, bool EXACT>
-__device__ __forceinline__ void build_table_row(float tick, const float2* __restrict__ s_coef, float* __restrict__ row)
-{
-    constexpr int KP = table_row_floats(K);
-    float l[KP];
-    float cum = 0.0f;
-    if constexpr (EXACT) {
-        float m = -INFINITY;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float2 ca = s_coef[k];
-            l[k] = __fsub_rn(ca.x, __fmul_rn(ca.y, tick));
-            m = fmaxf(m, l[k]);
-        }
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            cum = __fadd_rn(cum, soft_exp2(__fsub_rn(l[k], m)));
-            l[k] = cum;
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float2 ca = s_coef[k];
-            cum += fast_exp2(fmaf(-ca.y, tick, ca.x));
-            l[k] = cum;
-        }
-    }
-#pragma unroll
-    for (int k = K; k < KP; ++k) l[k] = cum;
-#pragma unroll
-    for (int k = 0; k < KP; ++k) row[k] = l[k];
-}
-
-// label of one datum from its memoised row; returns true if the row underflowed (FAST only).
-// The inverse-CDF search runs directly on the row in shared memory: log2(KP) dependent 4-byte
-// loads instead of fetching the whole row and searching it in registers.  Entries past K hold the
-// total, which never compares <= thr (thr < total), so they act as +inf padding; within a warp the
-// data are neighbours in tick order, hence mostly the same row and a handful of distinct addresses.
-// Returns 4 * (number of row entries <= u * total), i.e. the label as a byte offset into the
-// statistics array, and the row total.
-template <int K>
-__device__ __forceinline__ uint32_t search_row(uint32_t tick, float f12, const TableView& tab, float& total)
-{
-    constexpr int KP = table_row_floats(K);
-    constexpr int TOP = (KP > 16) ? 32 : (KP > 8) ? 16 : (KP > 4) ? 8 : 4;      // power of two >= KP
-    const uint32_t row = tab.addr + (tick - tab.lo) * (uint32_t)(4 * table_row_stride(K));
-    total = lds_f32<4 * (KP - 1)>(row);
-    const float thr = __fmaf_rn(f12, total, -total);
-    uint32_t p = row;                                      // row + 4 * (number of entries <= thr found so far)
-#define BRTA_PROBE(STEP)                                                                          \
-    if constexpr (TOP / 2 >= STEP) {                                                                  \
-        const float v = lds_f32<4 * (STEP - 1)>(p);                                                   \
-        /* rows are KP long: probes past the end count as +inf */                                     \
-        const bool in_row = (TOP == KP) || (p + 4u * (STEP - 1) < row + 4u * KP);                     \
-        if (in_row && v <= thr) p += 4u * STEP;                                                       \
-    }
-    BRTA_PROBE(16) BRTA_PROBE(8) BRTA_PROBE(4) BRTA_PROBE(2) BRTA_PROBE(1)
-#undef BRTA_PROBE
-    return p - row;
-}
-
-// FAST mode: a total below 2^-90 (every term underflowed) sends the datum to draw_label_safe
-constexpr float TOTAL_FLOOR = 8.0779357e-28f;
-
-template <int K>
-__device__ __forceinline__ bool label_from_table(uint32_t tick, float f12, const TableView& tab, int kmax, int& lab)
-{
-    float total;
-    lab = min((int)(search_row<K>(tick, f12, tab, total) >> 2), kmax);
-    return !(total > TOTAL_FLOOR);
-}
-
-// One quad (4 data) of the sweep: labels, statistics, optional label store.
-//
-// Statistics: shared-memory atomics for every label except the currently dominant one
-// (`dom`, the most populated component of the previous iteration), whose statistics follow
-// by subtraction from the slice totals -- exact integer arithmetic, so any choice of `dom`
-// gives the same result; skipping it removes most of the same-address contention.
-// integer tick -> float32 without the XU pipe: 2^23 + tick is exact for tick < 2^23
-__device__ __forceinline__ float tick_to_float(uint32_t tick)
-{
-    return __uint_as_float(0x4B000000u | tick) - 8388608.0f;
-}
-
-template <int K, bool EXACT, bool SAVE>
-__device__ __forceinline__ void sweep_quad(const uint4 tk, const float4 f12, const float2* __restrict__ s_coef,
-                                           int kmax, int dom, int i0, int n_data, bool partial,
-                                           uint32_t stat_addr, uint8_t* ind_row, const int32_t* __restrict__ perm,
-                                           const TableView& tab)
-{
-    constexpr int D = data_in_flight(K);
-    const uint32_t tis[4] = {tk.x, tk.y, tk.z, tk.w};
-    float tks[4];
-    const float fs[4] = {f12.x, f12.y, f12.z, f12.w};      // uniforms as floats in [1,2)
-    int labs[4];
-    unsigned redo = 0u;
-    if (!partial && max(max(tk.x, tk.y), max(tk.z, tk.w)) < tab.limit) {
-#pragma unroll
-        for (int d = 0; d < 4; ++d)                        // memoised rows: same bits as the direct path
-            if (label_from_table<K>(tis[d], fs[d], tab, kmax, labs[d])) redo |= 1u << d;
-    } else {
-#pragma unroll
-        for (int d = 0; d < 4; ++d) tks[d] = tick_to_float(tis[d]);
-#pragma unroll
-        for (int h = 0; h < 4; h += D) {
-            float td[D], fd[D];
-            int ld[D];
-#pragma unroll
-            for (int d = 0; d < D; ++d) { td[d] = tks[h + d]; fd[d] = fs[h + d]; }
-            redo |= draw_labels<K, D, EXACT>(td, fd, s_coef, kmax, ld) << h;
-#pragma unroll
-            for (int d = 0; d < D; ++d) labs[h + d] = ld[d];
-        }
-    }
-    if (redo) {                                            // cold: after the quad, few registers are live
-#pragma unroll
-        for (int d = 0; d < 4; ++d)
-            if (redo & (1u << d)) labs[d] = draw_label_safe<K>(tick_to_float(tis[d]), fs[d], s_coef, kmax);
-    }
-    if (partial) {                                         // the chain's last quad: padding is never counted
-#pragma unroll
-        for (int d = 0; d < 4; ++d)
-            if (i0 + d >= n_data) labs[d] = dom;
-    }
-#pragma unroll
-    for (int d = 0; d < 4; ++d)
-        if (labs[d] != dom)                                // ATOMS cost scales with the active lanes
-            red_shared_stats(stat_addr + 4u * (uint32_t)labs[d], tis[d]);
-    if (SAVE) {                                            // 1 iteration in `thin`: dense [S,N] bytes
-#pragma unroll
-        for (int d = 0; d < 4; ++d)
-            if (i0 + d < n_data) ind_row[perm ? perm[i0 + d] : i0 + d] = (uint8_t)labs[d];
-    }
-}
-
-// U quads of the served prefix at once: U Philox blocks and 4U row searches in flight per thread.
-// The chain of dependent shared-memory loads of one search is what the warp waits for; with
-// only four CTAs of four warps per SM the extra independent work is what fills those slots.
-#ifndef BRTA_SERVED_UNROLL
-#define BRTA_SERVED_UNROLL 2
-#endif
-template <int K, bool SAVE, bool T16, int U>
-__device__ __forceinline__ void sweep_served(uint32_t slice_addr, int q0, int qb, int kmax, int dom, uint32_t j,
-                                             uint32_t chain_id, const RoundKeys& rk, uint32_t stat_addr,
-                                             uint8_t* ind_row, const int32_t* __restrict__ perm, const TableView& tab,
-                                             const float2* __restrict__ s_coef)
-{
-    uint32_t tis[U][4];
-    float fs[U][4];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const int q = q0 + u * THREADS;
-        const uint4 tk = lds_quad<T16>(slice_addr, q);
-        tis[u][0] = tk.x; tis[u][1] = tk.y; tis[u][2] = tk.z; tis[u][3] = tk.w;
-        const Words4 w = philox4x32_10_rk((uint32_t)(qb + q), j, chain_id, 0u, rk);
-        fs[u][0] = word_to_12(w.x); fs[u][1] = word_to_12(w.y); fs[u][2] = word_to_12(w.z); fs[u][3] = word_to_12(w.w);
-    }
-    // label as byte offset 4 * k.  With a usable row (0 < total < inf) the last real entry equals the
-    // total and u * total < total, so the count never passes K - 1 and needs no clamp.
-    uint32_t off[U][4];
-    float lowest = INFINITY;
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int d = 0; d < 4; ++d) {
-            float total;
-            off[u][d] = search_row<K>(tis[u][d], fs[u][d], tab, total);
-            lowest = fminf(lowest, total);
-        }
-    if (!(lowest > TOTAL_FLOOR)) {                         // cold: a row underflowed (FAST mode only)
-        constexpr int KP = table_row_floats(K);
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int d = 0; d < 4; ++d) {
-                const float total = lds_f32<4 * (KP - 1)>(tab.addr + (tis[u][d] - tab.lo) * (uint32_t)(4 * table_row_stride(K)));
-                if (!(total > TOTAL_FLOOR))
-                    off[u][d] = 4u * (uint32_t)draw_label_safe<K>(tick_to_float(tis[u][d]), fs[u][d], s_coef, kmax);
-            }
-    }
-    const uint32_t dom_off = 4u * (uint32_t)dom;
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-#pragma unroll
-        for (int d = 0; d < 4; ++d)
-            if (off[u][d] != dom_off) red_shared_stats(stat_addr + off[u][d], tis[u][d]);
-    if (SAVE) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int i0 = (qb + q0 + u * THREADS) * 4;        // served quads are full quads
-#pragma unroll
-            for (int d = 0; d < 4; ++d) ind_row[perm ? perm[i0 + d] : i0 + d] = (uint8_t)(off[u][d] >> 2);
-        }
-    }
-}
-
-// One iteration's sweep over a staged slice (`slice_addr`: its shared-window address).
-// `n_served`: the first n_served quads are full quads with every tick inside the memoised rows
-// (with the chain in ascending-tick order: all the served quads); they run U at a time without
-// any per-quad case distinction, the rest through sweep_quad.
-template <int K, bool EXACT, bool SAVE, bool T16>
-__device__ __forceinline__ void sweep_slice_t(uint32_t slice_addr, const float2* __restrict__ s_coef,
-                                              int nq, int qb, int n_data, int kmax, int dom, uint32_t j,
-                                              uint32_t chain_id, const RoundKeys& rk,
-                                              const float4* __restrict__ u_row, uint32_t stat_addr,
-                                              uint8_t* ind_row, const int32_t* __restrict__ perm, const TableView& tab,
-                                              int n_served)
-{
-    constexpr int U = BRTA_SERVED_UNROLL;
-    int q_done = 0;
-    if (u_row == nullptr) {                                // injected uniforms (tests) take the general loop
-        q_done = n_served / (U * THREADS) * (U * THREADS);
-        for (int q = threadIdx.x; q < q_done; q += U * THREADS)
-            sweep_served<K, SAVE, T16, U>(slice_addr, q, qb, kmax, dom, j, chain_id, rk, stat_addr, ind_row, perm, tab, s_coef);
-        if constexpr (U > 1) {
-            const int q_one = n_served / THREADS * THREADS;
-            for (int q = q_done + threadIdx.x; q < q_one; q += THREADS)
-                sweep_served<K, SAVE, T16, 1>(slice_addr, q, qb, kmax, dom, j, chain_id, rk, stat_addr, ind_row, perm, tab, s_coef);
-            q_done = q_one;
-        }
-    }
-    // at most one quad of the whole chain is partial; find out once whether it is in this slice
-    const int tail_q = ((n_data & 3) != 0) ? (n_data >> 2) - qb : -1;
-    for (int q = q_done + threadIdx.x; q < nq; q += THREADS) {
-        const uint4 tk = lds_quad<T16>(slice_addr, q);
-        float4 f12;
-        if (u_row != nullptr) {
-            const float4 uu = u_row[qb + q];
-            f12 = make_float4(uu.x + 1.0f, uu.y + 1.0f, uu.z + 1.0f, uu.w + 1.0f);
-        } else {
-            const Words4 w = philox4x32_10_rk((uint32_t)(qb + q), j, chain_id, 0u, rk);
-            f12 = make_float4(word_to_12(w.x), word_to_12(w.y), word_to_12(w.z), word_to_12(w.w));
-        }
-        sweep_quad<K, EXACT, SAVE>(tk, f12, s_coef, kmax, dom, (qb + q) * 4, n_data, q == tail_q,
-                                   stat_addr, ind_row, perm, tab);
-    }
-}
-
-template <int K, bool EXACT, bool SAVE>
-__device__ __forceinline__ void sweep_slice(uint32_t slice_addr, bool ticks16, const float2* __restrict__ s_coef,
-                                            int nq, int qb, int n_data, int kmax, int dom, uint32_t j,
-                                            uint32_t chain_id, const RoundKeys& rk,
-                                            const float4* __restrict__ u_row, uint32_t stat_addr,
-                                            uint8_t* ind_row, const int32_t* __restrict__ perm, const TableView& tab,
-                                            int n_served)
-{
-    if (ticks16)
-        sweep_slice_t<K, EXACT, SAVE, true>(slice_addr, s_coef, nq, qb, n_data, kmax, dom, j, chain_id, rk, u_row,
-                                            stat_addr, ind_row, perm, tab, n_served);
-    else
-        sweep_slice_t<K, EXACT, SAVE, false>(slice_addr, s_coef, nq, qb, n_data, kmax, dom, j, chain_id, rk, u_row,
-                                             stat_addr, ind_row, perm, tab, n_served);
-}
-
-// length of the served prefix of a staged slice: the first quad that is partial or has a tick
-// outside [lo, limit) ends it.  Block-wide; `s_scratch` holds WARPS words.
-__device__ __forceinline__ int served_prefix(const unsigned char* __restrict__ s_ticks, bool ticks16, int nq, int qb,
-                                             int n_data, unsigned limit, unsigned* s_scratch)
-{
-    unsigned first = (unsigned)nq;
-    for (int q = threadIdx.x; q < nq; q += THREADS) {
-        unsigned hi;
-        if (ticks16) {
-            const uint2 raw = reinterpret_cast<const uint2*>(s_ticks)[q];
-            hi = max(max(raw.x & 0xffffu, raw.x >> 16), max(raw.y & 0xffffu, raw.y >> 16));
-        } else {
-            const uint4 raw = reinterpret_cast<const uint4*>(s_ticks)[q];
-            hi = max(max(raw.x, raw.y), max(raw.z, raw.w));
-        }
-        if ((qb + q) * 4 + 3 >= n_data || hi >= limit) { first = (unsigned)q; break; }
-    }
-    first = __reduce_min_sync(FULL, first);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) s_scratch[threadIdx.x >> 5] = first;
-    __syncthreads();
-    unsigned r = s_scratch[0];
-#pragma unroll
-    for (int w = 1; w < WARPS; ++w) r = min(r, s_scratch[w]);
-    __syncthreads();
-    return (int)r;
-}
-
-// Developer-only phase timing (-DBRTA_PHASE_TIMING builds a debug library): thread 0 of
-// every CTA accumulates clock64 deltas per phase into g_phase[blockIdx.x][8].
-#ifdef BRTA_PHASE_TIMING
-__device__ unsigned long long* g_phase = nullptr;
-#define PHASE_DECL long long ph_t = clock64(); unsigned long long ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#define PHASE_MARK(i) do { if (threadIdx.x == 0) { const long long now = clock64(); ph_acc[i] += (unsigned long long)(now - ph_t); ph_t = now; } } while (0)
-#define PHASE_FLUSH do { if (threadIdx.x == 0 && g_phase) for (int i = 0; i < 8; ++i) g_phase[blockIdx.x * 8 + i] += ph_acc[i]; } while (0)
-#else
-#define PHASE_DECL
-#define PHASE_MARK(i)
-#define PHASE_FLUSH
-#endif
-
-__device__ __forceinline__ bool coef_ok(float2 ca)
-{
-    return (ca.x == ca.x) && (ca.x < INFINITY) && (ca.y >= 0.0f) && (ca.y < INFINITY);
-}
-
-__device__ __forceinline__ void named_barrier_sync(int id, int nthreads)
-{
-    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
-}
-
-// co-resident CTAs per SM the register budget is capped for: the serial section of one
-// CTA (exchange + posterior draw) is hidden by the sweeps of the others
-#ifndef BRTA_MIN_CTAS_SMALLK
-#define BRTA_MIN_CTAS_SMALLK (512 / THREADS)
-#endif
-#ifndef BRTA_MIN_CTAS_LARGEK
-#define BRTA_MIN_CTAS_LARGEK (384 / THREADS)
-#endif
-constexpr int min_ctas(int k) { return k <= 16 ? BRTA_MIN_CTAS_SMALLK : BRTA_MIN_CTAS_LARGEK; }
-
-template <int K, bool EXACT>
-__global__ void __launch_bounds__(THREADS, min_ctas(K))
-gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
-{
-    const brta_batch& b = prm.b;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-
-
-    __shared__ __align__(16) float2 s_coef[32];            // {coef_c, coef_a}
-    // this CTA's statistics of the running iteration: [0..31] n_k, [32..63] biased tick sums
-    // (true sums fit 32 bits: host-checked)
-    __shared__ __align__(16) unsigned s_stat[64];
-    unsigned* const s_cnt = s_stat;
-    unsigned* const s_sum = s_stat + 32;
-    __shared__ __align__(16) float s_table[TABLE_FLOATS + 32];  // memoised cumulative rows of the running iteration (+ probe overrun)
-    const uint32_t stat_addr = opaque_u32((uint32_t)__cvta_generic_to_shared(s_stat));
-    const uint32_t slice_addr = opaque_u32((uint32_t)__cvta_generic_to_shared(smem_raw));
-    const uint32_t table_addr = opaque_u32((uint32_t)__cvta_generic_to_shared(s_table));
-    __shared__ unsigned s_red_lo[WARPS], s_red_hi[WARPS];  // smallest / largest tick of the slice
-    __shared__ unsigned long long s_red_t[WARPS];
-    __shared__ unsigned s_red_n[WARPS];
-    __shared__ int s_dom;
-    __shared__ unsigned s_tot_c[WARPS][32];                // team totals, one row per gathering warp
-    __shared__ unsigned long long s_tot_s[WARPS][32];
-    __shared__ float s_try_g[2][NTRIALS][32];              // parallel Marsaglia-Tsang trials: d*v or NaN
-    __shared__ float s_try_b[2][NTRIALS][32];              //   and log2 of the shape < 1 boost uniform
-    __shared__ unsigned s_bad;
-    __shared__ unsigned s_abort;                           // rendezvous watchdog tripped
-
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    // The warp that runs the serial part of an iteration (partials, posterior).  Warp w of every CTA sits on
-    // SM sub-partition w % 4; rotating the role over the co-resident CTAs (blockIdx b, b + grid/4, ... or
-    // 4m .. 4m+3, whichever the block scheduler chose) spreads the serial work over the four schedulers.
-    const int lead = (int)((blockIdx.x + blockIdx.x / max(gridDim.x >> 2, 1u)) & (WARPS - 1));
-    const uint32_t key0 = (uint32_t)b.seed;
-    const uint32_t key1 = (uint32_t)(b.seed >> 32);
-    const int kreal = b.ncomp;
-    const int niter = b.niter;
-    const int thin = b.thin;
-    const int rows = (niter + 1) / thin;
-    const int j_begin = b.iter_begin;                        // this launch runs iterations j_begin + 1 .. j_end
-    const int j_end = b.iter_end > 0 ? b.iter_end : niter;
-    const bool inject_coef = (b.flags & BRTA_FLAG_INJECT_COEF) != 0;
-    const bool inject_u = (b.flags & BRTA_FLAG_INJECT_U) != 0;
-    const bool trace = (b.flags & BRTA_FLAG_TRACE) != 0;
-
-    const int task_end = b.cta_task_begin[blockIdx.x + 1];
-    for (int ti = b.cta_task_begin[blockIdx.x]; ti < task_end; ++ti) {
-        const brta_task task = b.tasks[ti];
-        const int r = task.chain;
-        const int n_data = b.n_data[r];
-        const int nq = task.quad_count;
-        const int qb = task.quad_begin;
-        const int team = task.team_size;
-        const int n_shards = b.n_shards > 1 ? b.n_shards : 1;
-        const bool sharded = n_shards > 1;                 // the chain continues on other GPUs
-        const bool mailbox = !sharded && team > 1 && team <= BRTA_MAILBOX_MAX_TEAM;
-        const uint32_t chain_id = b.chain_id[r];
-        // a chain whose largest tick fits 16 bits keeps its slice in shared memory at 8 B per quad
-        const bool ticks16 = b.max_tick[r] < 65536u;
-        const float ts = b.ts[r];
-        const int64_t tick_off = b.tick_offset[r];
-        const int ind_stride = b.ind_stride[r];
-        uint8_t* const ind_base = b.indicator + b.ind_offset[r];
-        const int32_t* const perm = b.perm ? b.perm + b.perm_offset[r] : nullptr;
-        const float* const inj_u_base = inject_u ? b.inj_u + b.inj_u_offset[r] : nullptr;
-        const size_t u_pitch = (size_t)((n_data + 3) / 4) * 4;
-
-        // ---- stage the slice: integer ticks into shared memory, slice totals, tick range ----
-        unsigned my_n = 0, my_lo = 0xffffffffu, my_hi = 0u;
-        unsigned long long my_t = 0;
-        for (int q = tid; q < nq; q += THREADS) {
-            const int i0 = (qb + q) * 4;
-            unsigned t0, t1, t2, t3;
-            if (b.tick_bytes == 2) {
-                const ushort4 raw = reinterpret_cast<const ushort4*>(
-                    static_cast<const uint16_t*>(b.ticks) + tick_off)[qb + q];
-                t0 = raw.x; t1 = raw.y; t2 = raw.z; t3 = raw.w;
-            } else {
-                const uint4 raw = reinterpret_cast<const uint4*>(
-                    static_cast<const uint32_t*>(b.ticks) + tick_off)[qb + q];
-                t0 = raw.x; t1 = raw.y; t2 = raw.z; t3 = raw.w;
-            }
-            if (i0 + 3 < n_data) {                           // full quads only: the partial quad never uses the table
-                my_lo = min(my_lo, min(min(t0, t1), min(t2, t3)));
-                my_hi = max(my_hi, max(max(t0, t1), max(t2, t3)));
-            }
-            if (i0 + 0 >= n_data) t0 = 0;
-            if (i0 + 1 >= n_data) t1 = 0;
-            if (i0 + 2 >= n_data) t2 = 0;
-            if (i0 + 3 >= n_data) t3 = 0;
-            my_n += (unsigned)min(4, max(0, n_data - i0));
-            my_t += (unsigned long long)t0 + t1 + t2 + t3;
-            if (ticks16) reinterpret_cast<uint2*>(smem_raw)[q] = make_uint2(t0 | (t1 << 16), t2 | (t3 << 16));
-            else reinterpret_cast<uint4*>(smem_raw)[q] = make_uint4(t0, t1, t2, t3);
-        }
-        my_n = __reduce_add_sync(FULL, my_n);
-        my_t = warp_sum_u64(my_t);
-        my_lo = __reduce_min_sync(FULL, my_lo);
-        my_hi = __reduce_max_sync(FULL, my_hi);
-        if (lane == 0) { s_red_n[warp] = my_n; s_red_t[warp] = my_t; s_red_lo[warp] = my_lo; s_red_hi[warp] = my_hi; }
-        if (tid < 32) {
-            float2 ca = make_float2(-INFINITY, 0.0f);
-            if (tid < kreal && !inject_coef)
-                ca = make_float2(b.init_c[(size_t)r * kreal + tid], b.init_a[(size_t)r * kreal + tid]);
-            s_coef[tid] = ca;
-            s_cnt[tid] = 0;
-            s_sum[tid] = 0;
-        }
-        s_tot_c[warp][lane] = 0;
-        s_tot_s[warp][lane] = 0;
-        if (tid == 0) { s_dom = 0; s_bad = 0; s_abort = 0; }
-        __syncthreads();
-
-        // slice totals (warp 0) and per-component priors, lane = component
-        unsigned slice_n = 0;
-        unsigned long long slice_t = 0;
-        float wh = 0.0f, rh_a = 1.0f, rh_b = 1.0f;
-        if (warp == lead) {
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) { slice_n += s_red_n[w]; slice_t += s_red_t[w]; }
-        }
-        if (lane < kreal) {
-            wh = b.whyper[(size_t)r * kreal + lane];
-            rh_a = b.rhyper[((size_t)r * kreal + lane) * 2 + 0];
-            rh_b = b.rhyper[((size_t)r * kreal + lane) * 2 + 1];
-        }
-        // memoised rows cover ticks lo .. lo + table_rows - 1 of this slice
-        unsigned tick_lo = 0xffffffffu, tick_hi = 0u;
-#pragma unroll
-        for (int w = 0; w < WARPS; ++w) { tick_lo = min(tick_lo, s_red_lo[w]); tick_hi = max(tick_hi, s_red_hi[w]); }
-        int table_rows = 0;
-        if (!(b.flags & BRTA_FLAG_NO_TABLE) && tick_lo <= tick_hi)
-            table_rows = (int)min((unsigned)(TABLE_FLOATS / table_row_stride(K)), tick_hi - tick_lo + 1u);
-        TableView tab;
-        tab.addr = table_addr;
-        tab.lo = tick_lo;
-        tab.limit = table_rows > 0 ? tick_lo + (unsigned)table_rows : 0u;
-        const int n_served = served_prefix(smem_raw, ticks16, nq, qb, n_data, tab.limit, s_red_lo);
-        unsigned char* const exch = static_cast<unsigned char*>(b.exchange) + b.exch_offset[r];
-        // mailbox layout: slot[parity][member][32] of {tag<<32 | n_k, tag<<32 | tick sum}
-        ulonglong2* const mbox = reinterpret_cast<ulonglong2*>(exch);
-        // atomics layout (teams larger than the mailbox limit)
-        unsigned long long* const ex_sum = reinterpret_cast<unsigned long long*>(exch + EXCH_SUM_OFF);
-        unsigned* const ex_cnt = reinterpret_cast<unsigned*>(exch + EXCH_CNT_OFF);
-        unsigned* const ex_arrive = reinterpret_cast<unsigned*>(exch + EXCH_ARRIVE_OFF);
-
-        bool bad = false;
-        unsigned long long busy_cycles = 0;                // schedule feedback: iteration start -> post
-        PHASE_DECL
-        for (int j = j_begin + 1; j <= j_end; ++j) {
-            const long long iter_t0 = b.task_cycles ? clock64() : 0;
-            if (inject_coef) {
-                if (tid < kreal) {
-                    const size_t o = ((size_t)r * niter + (j - 1)) * kreal + tid;
-                    const float2 ca = make_float2(b.inj_c[o], b.inj_a[o]);
-                    bad |= !coef_ok(ca);
-                    s_coef[tid] = ca;
-                }
-                __syncthreads();
-            }
-            if (table_rows > 0) {                          // cumulative rows of this iteration's coefficients
-                for (int rr = tid; rr < table_rows; rr += THREADS)
-                    build_table_row<K, EXACT>((float)(tick_lo + (unsigned)rr), s_coef,
-                                              s_table + (size_t)rr * table_row_stride(K));
-                __syncthreads();
-            }
-            const bool save = (j % thin == 0);
-            const int row = j / thin - 1;
-            const float4* const u_row = inject_u
-                ? reinterpret_cast<const float4*>(inj_u_base + (size_t)(j - 1) * u_pitch) : nullptr;
-
-            const int dom = s_dom;
-
-            // ---- indicator draws + sufficient statistics (gibbs.py:196-207) -------------
-            if (save)
-                sweep_slice<K, EXACT, true>(slice_addr, ticks16, s_coef, nq, qb, n_data, kreal - 1, dom, (uint32_t)j, chain_id,
-                                            prm.rk, u_row, stat_addr, ind_base + (size_t)row * ind_stride, perm, tab, n_served);
-            else
-                sweep_slice<K, EXACT, false>(slice_addr, ticks16, s_coef, nq, qb, n_data, kreal - 1, dom, (uint32_t)j, chain_id,
-                                             prm.rk, u_row, stat_addr, nullptr, nullptr, tab, n_served);
-            PHASE_MARK(0);                                 // sweep
-            __syncthreads();
-            PHASE_MARK(1);                                 // wait for the CTA's slowest warp
-            if (b.task_cycles && 2 * (j - j_begin) > j_end - j_begin) busy_cycles += (unsigned long long)(clock64() - iter_t0);
-
-            // ---- this CTA's partials; the uncounted dominant label follows by subtraction --
-            if (warp == lead) {
-                unsigned cnt = s_cnt[lane];
-                unsigned sum = s_sum[lane];
-                s_cnt[lane] = 0;
-                s_sum[lane] = 0;
-                const unsigned oc = __reduce_add_sync(FULL, cnt);
-                const unsigned os = __reduce_add_sync(FULL, sum);
-                if (lane == dom) { cnt = slice_n - oc; sum = (unsigned)(slice_t - os); }
-                if (team == 1 && !sharded) {
-                    s_tot_c[0][lane] = cnt;
-                    s_tot_s[0][lane] = sum;
-                } else if (mailbox) {
-                    if (lane < kreal) {
-                        const unsigned long long tag = (unsigned long long)(unsigned)j << 32;
-                        st_relaxed_v2(&mbox[((size_t)(j & 1) * team + task.team_rank) * 32 + lane],
-                                      tag | cnt, tag | sum);
-                    }
-                } else {
-                    // large team: L2 atomics + monotonic arrive counter (3 rotating buffers)
-                    const int buf = j % 3;
-                    if (cnt != 0u) {
-                        atomicAdd(&ex_cnt[buf * 32 + lane], cnt);
-                        atomicAdd(&ex_sum[buf * 32 + lane], (unsigned long long)sum);
-                    }
-                    __syncwarp();
-                    if (lane == 0) {
-                        __threadfence();
-                        atomicAdd(ex_arrive, 1u);
-                    }
-                    const unsigned target = (unsigned)team * (unsigned)(j - j_begin);   // the counter starts at 0 every launch
-                    unsigned spins = 0;
-                    while (ld_acquire_u32(ex_arrive) < target) {
-                        if (++spins > SPIN_LIMIT) { s_abort = 1u; break; }
-                        __nanosleep(spins < 64u ? 40 : 1000);
-                    }
-                    unsigned tot_c = ld_relaxed_u32(&ex_cnt[buf * 32 + lane]);
-                    unsigned long long tot_s = ld_relaxed_u64(&ex_sum[buf * 32 + lane]);
-                    if (task.team_rank == 0) {             // recycle the buffer last read in j-1
-                        const int old = (j + 2) % 3;
-                        ex_cnt[old * 32 + lane] = 0u;
-                        ex_sum[old * 32 + lane] = 0ull;
-                    }
-                    if (sharded) {
-                        // second level: this GPU's totals go to every GPU's mailbox over NVLink as tagged
-                        // 64-bit words {iteration | n_k}, {iteration | sum lo}, {iteration | sum hi}; the
-                        // local leader adds up all shards and publishes the result to the local team
-                        unsigned long long* const glob = reinterpret_cast<unsigned long long*>(b.shard_totals);
-                        unsigned* const glob_flag = reinterpret_cast<unsigned*>(
-                            static_cast<unsigned char*>(b.shard_totals) + 3 * 32 * 16);
-                        unsigned long long* const gslot = glob + ((size_t)(j % 3) * 32 + lane) * 2;
-                        if (task.team_rank == 0) {
-                            const unsigned long long tag = (unsigned long long)(unsigned)j << 32;
-                            const size_t slot = (((size_t)(j & 1) * n_shards + b.shard_rank) * 32 + lane) * 4;
-                            for (int g = 0; g < n_shards; ++g) {
-                                unsigned long long* const dst = static_cast<unsigned long long*>(b.shard_mailbox[g]) + slot;
-                                st_relaxed_sys_u64(dst + 0, tag | tot_c);
-                                st_relaxed_sys_u64(dst + 1, tag | (tot_s & 0xffffffffull));
-                                st_relaxed_sys_u64(dst + 2, tag | (tot_s >> 32));
-                            }
-                            const unsigned long long* const mine =
-                                static_cast<const unsigned long long*>(b.shard_mailbox[b.shard_rank]);
-                            unsigned all_c = 0;
-                            unsigned long long all_s = 0;
-                            for (int g = 0; g < n_shards; ++g) {
-                                const unsigned long long* const src = mine + (((size_t)(j & 1) * n_shards + g) * 32 + lane) * 4;
-                                unsigned long long w0, w1, w2;
-                                unsigned spins2 = 0;
-                                for (;;) {
-                                    w0 = ld_relaxed_sys_u64(src + 0);
-                                    w1 = ld_relaxed_sys_u64(src + 1);
-                                    w2 = ld_relaxed_sys_u64(src + 2);
-                                    if ((unsigned)(w0 >> 32) == (unsigned)j && (unsigned)(w1 >> 32) == (unsigned)j &&
-                                        (unsigned)(w2 >> 32) == (unsigned)j) break;
-                                    if (++spins2 > SPIN_LIMIT) { s_abort = 1u; break; }
-                                    __nanosleep(spins2 < 64u ? 100 : 1000);
-                                }
-                                all_c += (unsigned)w0;
-                                all_s += (w1 & 0xffffffffull) | (w2 << 32);
-                            }
-                            tot_c = all_c;
-                            tot_s = all_s;
-                            gslot[0] = tot_c;
-                            gslot[1] = tot_s;
-                            __syncwarp();
-                            if (lane == 0) {
-                                __threadfence();
-                                st_release_u32(glob_flag, (unsigned)j);
-                            }
-                        } else {
-                            unsigned spins2 = 0;
-                            while (ld_acquire_u32(glob_flag) < (unsigned)j) {
-                                if (++spins2 > SPIN_LIMIT) { s_abort = 1u; break; }
-                                __nanosleep(spins2 < 64u ? 100 : 1000);
-                            }
-                            tot_c = (unsigned)ld_relaxed_u64(gslot + 0);
-                            tot_s = ld_relaxed_u64(gslot + 1);
-                        }
-                    }
-                    s_tot_c[0][lane] = tot_c;
-                    s_tot_s[0][lane] = tot_s;
-                }
-            }
-            PHASE_MARK(2);                                 // partials + post
-            // shape-independent half of this warp's Marsaglia-Tsang trial, overlapped with the exchange
-            const int draw_type = warp & 1;                // 0: Dirichlet gamma (weights), 1: rate gamma
-            TrialRandoms rnd = {};
-            if (!inject_coef)
-                rnd = trial_randoms(philox4x32_10_rk((uint32_t)(warp >> 1), (uint32_t)j, chain_id,
-                                                     (draw_type == 0 ? 1u : 2u) + 4u * lane, prm.rk));
-            if (mailbox) {
-                // every warp gathers a share of the members: lane = component, all loads of a
-                // round in flight together; a word is valid once it carries this iteration's tag
-                constexpr int MAXM = (BRTA_MAILBOX_MAX_TEAM + WARPS - 1) / WARPS;
-                unsigned acc_c = 0;
-                unsigned long long acc_s = 0;
-                if (lane < kreal) {
-                    const ulonglong2* const base = &mbox[(size_t)(j & 1) * team * 32 + lane];
-                    unsigned pend = 0;
-#pragma unroll
-                    for (int i = 0; i < MAXM; ++i)
-                        if (warp + i * WARPS < team) pend |= 1u << i;
-                    unsigned spins = 0;
-                    while (pend) {
-                        ulonglong2 v[MAXM];
-#pragma unroll
-                        for (int i = 0; i < MAXM; ++i)
-                            if (pend & (1u << i)) v[i] = ld_relaxed_v2(&base[(size_t)(warp + i * WARPS) * 32]);
-#pragma unroll
-                        for (int i = 0; i < MAXM; ++i) {
-                            if ((pend & (1u << i)) && (unsigned)(v[i].x >> 32) == (unsigned)j &&
-                                (unsigned)(v[i].y >> 32) == (unsigned)j) {
-                                acc_c += (unsigned)v[i].x;
-                                acc_s += (unsigned)v[i].y;
-                                pend &= ~(1u << i);
-                            }
-                        }
-                        if (pend) {
-                            // watchdog: a teammate that never posts (a scheduling bug, a lost GPU) must
-                            // not hang the device; legitimate waits (a teammate still finishing its
-                            // previous wave) are seconds at most
-                            if (++spins > SPIN_LIMIT) { s_abort = 1u; break; }
-                            __nanosleep(spins < 64u ? 20 : 1000);
-                        }
-                    }
-                }
-                s_tot_c[warp][lane] = acc_c;
-                s_tot_s[warp][lane] = acc_s;
-            }
-            PHASE_MARK(3);                                 // gather (waits for the team's slowest member)
-            __syncthreads();
-            PHASE_MARK(4);
-            if (s_abort) break;                            // uniform: written before the barrier
-
-            // ---- posterior update (gibbs.py:210-211) ----------------------------------------
-            // Every warp runs ONE Marsaglia-Tsang trial per component, straight-line: even
-            // warps for the Dirichlet gammas, odd warps for the rate gammas, warp >> 1 = trial
-            // index.  Warp 0 then takes, per component, the first accepted trial -- the same
-            // variate a sequential rejection loop would return, without its latency.
-            {
-                unsigned cnt = 0;
-                unsigned long long sum = 0;
-#pragma unroll
-                for (int w = 0; w < WARPS; ++w) { cnt += s_tot_c[w][lane]; sum += s_tot_s[w][lane]; }
-                const bool live = lane < kreal;
-                const float fcnt = (float)cnt;
-                const float shape = (draw_type == 0 ? wh : rh_a) + fcnt;
-                if (!inject_coef) {
-                    const GammaTrial t = trial_finish(shape < 1.0f ? shape + 1.0f : shape, rnd);
-                    s_try_g[draw_type][warp >> 1][lane] = t.ok ? t.g : __int_as_float(0x7fc00000);
-                    s_try_b[draw_type][warp >> 1][lane] = rnd.l2_boost;
-                }
-                PHASE_MARK(5);                             // gamma trials
-                __syncthreads();
-                if (warp == lead) {
-                    if (trace && task.team_rank == 0 && live) {
-                        const size_t o = ((size_t)r * niter + (j - 1)) * kreal + lane;
-                        b.trace_nk[o] = (int64_t)cnt;
-                        b.trace_tk[o] = (int64_t)sum;
-                    }
-                    // next iteration skips the most populated label in the atomics
-                    const unsigned keyv = live ? ((cnt << 5) | (unsigned)(31 - lane)) : 0u;
-                    const unsigned best = __reduce_max_sync(FULL, keyv);
-                    if (lane == 0) s_dom = 31 - (int)(best & 31u);
-                    if (!inject_coef) {
-                        float g[2], l2b[2];
-                        const float shapes[2] = {wh + fcnt, rh_a + fcnt};
-#pragma unroll
-                        for (int ty = 0; ty < 2; ++ty) {
-                            g[ty] = __int_as_float(0x7fc00000);
-                            l2b[ty] = 0.0f;
-#pragma unroll
-                            for (int tr = NTRIALS - 1; tr >= 0; --tr) {
-                                const float cand = s_try_g[ty][tr][lane];
-                                if (cand == cand) { g[ty] = cand; l2b[ty] = s_try_b[ty][tr][lane]; }
-                            }
-                            if (live && !(g[ty] == g[ty]))     // all parallel trials rejected (rare): go on serially
-                                g[ty] = gamma_serial(shapes[ty] < 1.0f ? shapes[ty] + 1.0f : shapes[ty], NTRIALS,
-                                                     (uint32_t)j, chain_id, (ty == 0 ? 1u : 2u) + 4u * lane, key0, key1, l2b[ty]);
-                        }
-                        // shape < 1 boost G(a) = G(a+1) U^(1/a): in log2 space for the weights (U^K underflows)
-                        float l2y = -INFINITY, rate = 0.0f;
-                        if (live) {
-                            l2y = __log2f(g[0]);
-                            if (shapes[0] < 1.0f) l2y += __fdividef(l2b[0], shapes[0]);
-                            float gr = g[1];
-                            if (shapes[1] < 1.0f) gr *= fast_exp2(__fdividef(l2b[1], shapes[1]));
-                            rate = __fdividef(gr, fmaf((float)sum, ts, rh_b));
-                        }
-                        const float mx = warp_max(l2y);
-                        const float tot = warp_sum(live ? fast_exp2(l2y - mx) : 0.0f);
-                        const float l2w = l2y - mx - __log2f(tot);
-                        const float2 ca = make_float2(l2w + __log2f(rate), rate * (ts * LOG2E));
-                        if (live) s_coef[lane] = ca;
-                        // a usable row: every slope finite and >= 0, every intercept finite or -inf (a dead
-                        // component), at least one alive -- then each datum's max term is exactly 1
-                        bad |= (live && !coef_ok(ca)) || !__any_sync(FULL, live && ca.x > -INFINITY);
-                        if (save && task.team_rank == 0 && live && row < rows) {
-                            const size_t o = ((size_t)r * rows + row) * kreal + lane;
-                            b.mcweights[o] = exp2((double)l2w);
-                            b.mcrates[o] = (double)rate;
-                        }
-                    }
-                }
-            }
-            PHASE_MARK(6);                                 // normalise + coefficients
-            __syncthreads();
-            PHASE_MARK(7);
-        }
-        PHASE_FLUSH;
-        if (b.task_cycles && tid == 0) b.task_cycles[ti] = busy_cycles;
-        if (b.final_c && b.final_a && task.team_rank == 0 && tid < kreal) {   // state for a following launch
-            b.final_c[(size_t)r * kreal + tid] = s_coef[tid].x;
-            b.final_a[(size_t)r * kreal + tid] = s_coef[tid].y;
-        }
-        if (bad) atomicOr(&s_bad, 1u);
-        __syncthreads();
-        if (tid == 0 && s_bad) atomicOr(reinterpret_cast<unsigned*>(&b.status[r]), (unsigned)BRTA_STATUS_NONFINITE);
-        if (tid == 0 && s_abort) atomicOr(reinterpret_cast<unsigned*>(&b.status[r]), (unsigned)BRTA_STATUS_TIMEOUT);
-        __syncthreads();
-    }
-}
 
 __global__ void philox_fill_kernel(uint32_t* out, int64_t n, uint32_t x0, uint32_t c1, uint32_t c2,
                                    uint32_t c3, uint32_t k0, uint32_t k1)
@@ -1092,31 +53,53 @@ int cuda_fail(cudaError_t e, const char* where)
     return (int)e;
 }
 
-typedef void (*kernel_fn)(const SweepParams);
+// Gamma-sampler probe: draw i takes shape shapes[i % n_shapes] and returns log2 of a Gamma(shape, 1)
+// variate produced by exactly the device functions of the sampler's posterior update (trial_randoms,
+// trial_finish, log2_gamma incl. the shape < 1 boost) on the Philox stream (trial, i, chain, purpose).
+__global__ void gamma_fill_kernel(float* out, int64_t n, const float* shapes, int n_shapes, uint32_t chain,
+                                  uint32_t purpose, uint32_t k0, uint32_t k1)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    TrialRandoms pre[NTRIALS];
+#pragma unroll
+    for (int t = 0; t < NTRIALS; ++t)
+        pre[t] = trial_randoms(philox4x32_10((uint32_t)t, (uint32_t)i, chain, purpose, k0, k1));
+    out[i] = log2_gamma<NTRIALS>(shapes[i % n_shapes], pre, (uint32_t)i, chain, purpose, k0, k1, true);
+}
 
-struct Variant {
-    int k;
-    kernel_fn fast, exact;
-    kernel_fn pick(uint32_t flags) const { return (flags & BRTA_FLAG_EXACT) ? exact : fast; }
-};
-
-#define BRTA_VARIANT(KK) {KK, gibbs_sweep_kernel<KK, false>, gibbs_sweep_kernel<KK, true>}
-const Variant g_variants[] = {
-#ifdef BRTA_ONLY_K15                                       // developer builds: one instantiation, fast compile
-    BRTA_VARIANT(15),
-#else
-    BRTA_VARIANT(2),  BRTA_VARIANT(3),  BRTA_VARIANT(4),  BRTA_VARIANT(5),  BRTA_VARIANT(6),
-    BRTA_VARIANT(8),  BRTA_VARIANT(10), BRTA_VARIANT(12), BRTA_VARIANT(15), BRTA_VARIANT(16),
-    BRTA_VARIANT(20), BRTA_VARIANT(24), BRTA_VARIANT(30), BRTA_VARIANT(32),
+#define BRTA_FOR_EACH_K(X) X(2) X(3) X(4) X(5) X(6) X(8) X(10) X(12) X(15) X(16) X(20) X(24) X(30) X(32)
+#ifdef BRTA_ONLY_K15                                       // developer builds: one instantiation
+#undef BRTA_FOR_EACH_K
+#define BRTA_FOR_EACH_K(X) X(15)
 #endif
-};
+#define BRTA_DECLARE(KK) Variant variant_k##KK();
+BRTA_FOR_EACH_K(BRTA_DECLARE)
 
 const Variant* pick_variant(int ncomp)
 {
-    for (const Variant& v : g_variants)
+#define BRTA_ENTRY(KK) variant_k##KK(),
+    static const Variant variants[] = {BRTA_FOR_EACH_K(BRTA_ENTRY)};
+    for (const Variant& v : variants)
         if (v.k >= ncomp) return &v;
     return nullptr;
 }
+
+// the ABI never leaves the calling thread on another device
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int device)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+    }
+    ~DeviceGuard()
+    {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
 
 }  // namespace brta
 
@@ -1150,7 +133,8 @@ int brta_gibbs_launch_info(int device, int ncomp, uint32_t flags, int slice_cap_
     const brta::Variant* v = brta::pick_variant(ncomp);
     if (ncomp < 1 || !v) return brta::fail(BRTA_E_NCOMP, "ncomp must be in 1..32");
     brta::kernel_fn fn = v->pick(flags);
-    cudaError_t e = cudaSetDevice(device);
+    brta::DeviceGuard guard(device);
+    cudaError_t e = guard.err;
     if (e != cudaSuccess) return brta::cuda_fail(e, "cudaSetDevice");
     const size_t smem = (size_t)slice_cap_quads * 16;
     e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1196,14 +180,18 @@ int brta_gibbs_run_batch(const brta_batch* batch, void* stream)
     if (b.n_shards > 1) {
         if (b.n_chains != 1 || b.n_shards > BRTA_MAX_SHARDS || b.shard_rank < 0 || b.shard_rank >= b.n_shards)
             return brta::fail(BRTA_E_RANGE, "sharded launch: n_chains must be 1 and 0 <= shard_rank < n_shards <= 16");
-        if (!b.shard_mailbox || !b.shard_totals)
-            return brta::fail(BRTA_E_NULL, "sharded launch needs shard_mailbox and shard_totals");
+        if (!b.shard_mailbox)
+            return brta::fail(BRTA_E_NULL, "sharded launch needs shard_mailbox");
     }
     if ((b.flags & BRTA_FLAG_TRACE) && (!b.trace_nk || !b.trace_tk))
         return brta::fail(BRTA_E_NULL, "TRACE needs trace_nk and trace_tk");
 
     brta::kernel_fn fn = v->pick(b.flags);
     const size_t smem = (size_t)b.slice_cap_quads * 16;
+    int device = b.device;
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return brta::fail(BRTA_E_DEVICE, "no current CUDA device");
+    brta::DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return brta::cuda_fail(guard.err, "cudaSetDevice");
     cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return brta::cuda_fail(e, "cudaFuncSetAttribute(smem)");
     brta::SweepParams prm;
@@ -1218,7 +206,8 @@ int brta_gibbs_run_batch(const brta_batch* batch, void* stream)
 
 int brta_enable_peer_access(int device, int peer)
 {
-    cudaError_t e = cudaSetDevice(device);
+    brta::DeviceGuard guard(device);
+    cudaError_t e = guard.err;
     if (e != cudaSuccess) return brta::cuda_fail(e, "cudaSetDevice");
     int can = 0;
     e = cudaDeviceCanAccessPeer(&can, device, peer);
@@ -1240,14 +229,6 @@ int brta_mufu_probe(float* sink_dev, int blocks, int iters, void* stream)
     return 0;
 }
 
-#ifdef BRTA_PHASE_TIMING
-int brta_debug_set_phase_buffer(void* dev_ptr)
-{
-    unsigned long long* p = (unsigned long long*)dev_ptr;
-    cudaError_t e = cudaMemcpyToSymbol(brta::g_phase, &p, sizeof(p));
-    return (int)e;
-}
-#endif
 
 int brta_philox_fill(uint32_t* out_dev, int64_t n, uint32_t x0, uint32_t c1, uint32_t c2, uint32_t c3,
                      uint64_t seed, void* stream)
@@ -1260,6 +241,82 @@ int brta_philox_fill(uint32_t* out_dev, int64_t n, uint32_t x0, uint32_t c1, uin
         out_dev, n, x0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return brta::cuda_fail(e, "philox_fill_kernel");
+    return 0;
+}
+
+int brta_gamma_fill(float* out_dev, int64_t n, const float* shapes_dev, int n_shapes, uint32_t chain,
+                    uint32_t purpose, uint64_t seed, void* stream)
+{
+    if (!out_dev || !shapes_dev) return brta::fail(BRTA_E_NULL, "brta_gamma_fill: a pointer is NULL");
+    if (n_shapes < 1) return brta::fail(BRTA_E_RANGE, "brta_gamma_fill: n_shapes >= 1");
+    if (n <= 0) return 0;
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    brta::gamma_fill_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
+        out_dev, n, shapes_dev, n_shapes, chain, purpose, (uint32_t)seed, (uint32_t)(seed >> 32));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return brta::cuda_fail(e, "gamma_fill_kernel");
+    return 0;
+}
+
+int brta_shard_mailbox_create(int device, int n_shards, void** dev_ptr, unsigned char* handle64)
+{
+    if (!dev_ptr || !handle64) return brta::fail(BRTA_E_NULL, "brta_shard_mailbox_create: a pointer is NULL");
+    if (n_shards < 1 || n_shards > BRTA_MAX_SHARDS) return brta::fail(BRTA_E_RANGE, "n_shards must be in 1..16");
+    static_assert(sizeof(cudaIpcMemHandle_t) == BRTA_IPC_HANDLE_BYTES, "IPC handle size");
+    brta::DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return brta::cuda_fail(guard.err, "cudaSetDevice");
+    void* p = nullptr;
+    const size_t bytes = BRTA_SHARD_MAILBOX_BYTES(n_shards);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return brta::cuda_fail(e, "cudaMalloc(shard mailbox)");
+    e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return brta::cuda_fail(e, "cudaIpcGetMemHandle"); }
+    memcpy(handle64, &h, sizeof(h));
+    *dev_ptr = p;
+    return 0;
+}
+
+int brta_shard_mailbox_open(int device, const unsigned char* handle64, void** dev_ptr)
+{
+    if (!dev_ptr || !handle64) return brta::fail(BRTA_E_NULL, "brta_shard_mailbox_open: a pointer is NULL");
+    brta::DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return brta::cuda_fail(guard.err, "cudaSetDevice");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    cudaError_t e = cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return brta::cuda_fail(e, "cudaIpcOpenMemHandle");
+    return 0;
+}
+
+int brta_shard_mailbox_clear(int device, void* dev_ptr, int n_shards, void* stream)
+{
+    if (!dev_ptr) return brta::fail(BRTA_E_NULL, "brta_shard_mailbox_clear: pointer is NULL");
+    brta::DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return brta::cuda_fail(guard.err, "cudaSetDevice");
+    cudaError_t e = cudaMemsetAsync(dev_ptr, 0, BRTA_SHARD_MAILBOX_BYTES(n_shards), (cudaStream_t)stream);
+    if (e != cudaSuccess) return brta::cuda_fail(e, "cudaMemsetAsync(shard mailbox)");
+    return 0;
+}
+
+int brta_shard_mailbox_close(int device, void* dev_ptr)
+{
+    brta::DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return brta::cuda_fail(guard.err, "cudaSetDevice");
+    cudaError_t e = cudaIpcCloseMemHandle(dev_ptr);
+    if (e != cudaSuccess) return brta::cuda_fail(e, "cudaIpcCloseMemHandle");
+    return 0;
+}
+
+int brta_shard_mailbox_destroy(int device, void* dev_ptr)
+{
+    brta::DeviceGuard guard(device);
+    if (guard.err != cudaSuccess) return brta::cuda_fail(guard.err, "cudaSetDevice");
+    cudaError_t e = cudaFree(dev_ptr);
+    if (e != cudaSuccess) return brta::cuda_fail(e, "cudaFree(shard mailbox)");
     return 0;
 }
 

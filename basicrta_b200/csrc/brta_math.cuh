@@ -62,17 +62,19 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 }
 
 // ---- Gamma(shape, 1) variates ---------------------------------------------------------
-// Marsaglia & Tsang (2000).  One Philox call per trial: words 0,1 -> Box-Muller normal,
-// 2 -> accept uniform, 3 -> boost uniform.  The squeeze test accepts ~92 % of the trials
-// without a logarithm; the exact test needs log(v) accurately (v is within 1e-3 of 1 for
-// the large shapes 1 + n_k), hence log1pf there and MUFU-grade intrinsics elsewhere.
-// A trial yields d*v with d = a - 1/3 for the (possibly boosted) shape a >= 1; the shape < 1
-// boost G(a) = G(a+1) U^(1/a) is applied by the caller (in log2 space for the weights: an
-// empty component has Dirichlet shape 1/K (gibbs.py:173), where U^K underflows float32).
-// The part of a trial that does not depend on the shape: computed while the team exchange is
-// still in flight, so only ~40 instructions remain on the critical path once n_k is known.
+// Marsaglia & Tsang (2000), returned as log2 of the variate (the sampler only ever needs
+// log2 w_k and log2 r_k).  One Philox call per trial: words 0,1 -> Box-Muller normal,
+// 2 -> accept uniform, 3 -> boost uniform.  A trial for the (possibly boosted) shape a >= 1 yields
+// d*v with d = a - 1/3, v = (1 + x)^3, x = z / sqrt(9 d); the shape < 1 boost G(a) = G(a+1) U^(1/a)
+// is applied in log2 space by the caller: an empty component has Dirichlet shape 1/K
+// (gibbs.py:173), where U^K underflows float32.
+//
+// The part of a trial that does not depend on the shape (TrialRandoms) is computed while the team
+// exchange is still in flight, so only the ~25 dependent instructions of trial_finish remain on the
+// critical path once n_k is known.
 struct TrialRandoms {
     float z;          // standard normal (Box-Muller, words 0 and 1)
+    float half_zz;    // z^2 / 2
     float u;          // accept uniform in (0,1) (word 2)
     float log_u;      // ln u
     float squeeze;    // 1 - 0.0331 z^4
@@ -90,43 +92,67 @@ __device__ __forceinline__ TrialRandoms trial_randoms(const Words4& w)
     r.u = word_to_unit_open(w.z);
     r.log_u = __logf(r.u);
     const float z2 = r.z * r.z;
+    r.half_zz = 0.5f * z2;
     r.squeeze = 1.0f - 0.0331f * z2 * z2;
     r.l2_boost = __log2f(word_to_unit_open_low(w.w));
     return r;
 }
 
-struct GammaTrial { float g; bool ok; };
+struct GammaTrial { float l2g; bool ok; };               // log2(d v), accepted?
 
-// Finish a trial for shape a >= 1: straight-line, both acceptance tests evaluated.  The exact
-// test needs log(v) accurately (v is within 1e-3 of 1 for the large shapes 1 + n_k): log1pf.
+// Finish a trial for shape a >= 1: straight-line, both acceptance tests evaluated.
+// Exact test: ln u < z^2/2 + d (1 - v + 3 ln(1 + x)).  For the large shapes 1 + n_k, x is tiny and the
+// right-hand side is the small remainder of two cancellations (3 ln(1+x) against 1 - v up to x^3, and
+// d * 4.5 x^2 against z^2/2 exactly, because 9 d c^2 = 1): for |x| < 1/8 it is evaluated as the series
+//     d x^4 (-3/4 + 3/5 x - 3/6 x^2 + ... + 3/11 x^7)        (truncation < 1e-7 relative)
+// -- no logarithm, no cancellation; otherwise 1 + x is far from 1 and the plain form is accurate.
 __device__ __forceinline__ GammaTrial trial_finish(float a, const TrialRandoms& r)
 {
     const float d = a - (1.0f / 3.0f);
     const float c = rsqrtf(9.0f * d);
     const float x = c * r.z;
     const float t = 1.0f + x;
+    const float l2t = __log2f(t);                         // NaN for t < 0: such trials are rejected
+    const float x2 = x * x;
+    float p = 3.0f / 11.0f;
+    p = fmaf(p, x, -3.0f / 10.0f);
+    p = fmaf(p, x, 3.0f / 9.0f);
+    p = fmaf(p, x, -3.0f / 8.0f);
+    p = fmaf(p, x, 3.0f / 7.0f);
+    p = fmaf(p, x, -3.0f / 6.0f);
+    p = fmaf(p, x, 3.0f / 5.0f);
+    p = fmaf(p, x, -3.0f / 4.0f);
+    const float rhs_small = d * (x2 * x2) * p;
     const float v = t * t * t;
-    const bool exact = r.log_u < 0.5f * r.z * r.z + d * (1.0f - v + 3.0f * log1pf(fmaxf(x, -0.999999f)));
-    return GammaTrial{d * v, (x > -1.0f) && (r.u < r.squeeze || exact)};
+    const float rhs_large = r.half_zz + d * (1.0f - v + (3.0f * 0.6931471805599453f) * l2t);
+    const float rhs = fabsf(x) < 0.125f ? rhs_small : rhs_large;
+    const bool ok = (t > 0.0f) && (r.u < r.squeeze || r.log_u < rhs);
+    return GammaTrial{__log2f(d) + 3.0f * l2t, ok};
 }
 
-// Sequential rejection loop from trial `first` on: the fallback after the parallel trials
-// (and the definition of the draw: the first accepted trial in counter order).
-__device__ __noinline__ float gamma_serial(float a, uint32_t first, uint32_t iter, uint32_t chain, uint32_t purpose,
-                                           uint32_t k0, uint32_t k1, float& l2_boost)
+// log2 of a Gamma(shape, 1) variate: the first accepted trial in counter order 0, 1, 2, ... of the
+// Philox stream (x = trial, iteration, chain, purpose).  Trials 0 .. NPRE-1 arrive precomputed.
+template <int NPRE>
+__device__ __forceinline__ float log2_gamma(float shape, const TrialRandoms (&pre)[NPRE], uint32_t iter,
+                                            uint32_t chain, uint32_t purpose, uint32_t k0, uint32_t k1, bool live)
 {
-    float result = a - (1.0f / 3.0f);                     // never reached in practice
-    l2_boost = -1.0f;
-    for (uint32_t trial = first; trial < first + 64u; ++trial) {
-        const TrialRandoms r = trial_randoms(philox4x32_10(trial, iter, chain, purpose, k0, k1));
-        const GammaTrial t = trial_finish(a, r);
-        if (t.ok) {
-            result = t.g;
-            l2_boost = r.l2_boost;
-            break;
+    const float a = shape < 1.0f ? shape + 1.0f : shape;
+    float l2g = 0.0f, l2b = 0.0f;
+    bool ok = false;
+#pragma unroll
+    for (int i = NPRE - 1; i >= 0; --i) {                 // lowest accepted trial wins
+        const GammaTrial t = trial_finish(a, pre[i]);
+        if (t.ok) { l2g = t.l2g; l2b = pre[i].l2_boost; ok = true; }
+    }
+    if (live && !ok) {                                    // all precomputed trials rejected (< 1 %): go on serially
+        for (uint32_t trial = NPRE; trial < NPRE + 64u; ++trial) {
+            const TrialRandoms r = trial_randoms(philox4x32_10(trial, iter, chain, purpose, k0, k1));
+            const GammaTrial t = trial_finish(a, r);
+            if (t.ok) { l2g = t.l2g; l2b = r.l2_boost; break; }
         }
     }
-    return result;
+    if (shape < 1.0f) l2g += __fdividef(l2b, shape);
+    return l2g;
 }
 
 }  // namespace brta

@@ -74,9 +74,8 @@ def coefficients(weights, rates, ts):
 
 
 def times_to_ticks(times, ts):
-    """Residence times -> integer tick counts.  Contact durations are multiples of the
-    trajectory time step (basicrta/contacts.py:222-229); anything else is rounded to the
-    grid and must stay within 1e-3 of a tick."""
+    """Residence times -> integer tick counts on the grid ``ts`` (strict: every time must lie within
+    1e-3 of a tick).  :func:`tick_grid` finds the grid of arbitrary data."""
     t = np.asarray(times, dtype=np.float64) / float(ts)
     ticks = np.rint(t)
     if len(ticks) and np.max(np.abs(t - ticks)) > 1e-3:
@@ -85,6 +84,56 @@ def times_to_ticks(times, ts):
     if len(ticks) and (ticks.min() < 0 or ticks.max() >= _cabi.TICK_LIMIT):
         raise ValueError(f'tick range exceeds [0, 2^23): max {ticks.max():.0f}')
     return ticks.astype(np.int64)
+
+
+GRID_TOL = 1e-3                 # a time counts as "on the grid" within this many ticks
+GRID_MAX_DIVISOR = 4096         # finest sub-multiple of the hint tried before the data count as continuous
+SLICE_SUM_DATA = 1 << 17        # the tick sum of this many of the largest data must stay below 2^32
+
+
+def _on_grid(t, grid, tol):
+    r = t / grid
+    return float(np.max(np.abs(r - np.rint(r)))) <= tol
+
+
+def tick_grid(times, ts_hint=None):
+    """The integer grid the device works on: ``(ticks int64, grid)`` with ``times ~= ticks * grid``.
+
+    The reference's ``ts`` (first non-zero gap of the sorted times, gibbs.py:147-151) is only a hint:
+    contact durations are multiples of the trajectory step dt (contacts.py:222-229), but the first
+    gap of a sparse residue is usually a MULTIPLE of dt ({0.3, 0.7, 0.8} gives ts = 0.4), so the grid is
+    the coarsest ``ts_hint / m`` (m = 1, 2, ...) every time is a multiple of.  Data on no such grid
+    (continuous times, e.g. the reference's ``util.simulate_hn``, util.py:596-608) are put on a
+    fixed-point grid of up to 2^23 - 1 levels of the largest time -- the resolution float32 offers --
+    coarsened if needed so that 32-bit per-slice tick sums cannot overflow; the returned ``ticks`` are
+    then a rounding of the data, exact on the grid returned.  ``self.ts`` of the pickle is untouched."""
+    t = np.asarray(times, dtype=np.float64)
+    if t.ndim != 1 or len(t) == 0:
+        raise ValueError('times must be a non-empty 1-D array')
+    if not np.all(np.isfinite(t)) or t.min() < 0:
+        raise ValueError('times must be finite and non-negative')
+    tmax = float(t.max())
+    if tmax <= 0:
+        raise ValueError('all times are zero')
+    tol = GRID_TOL if np.asarray(times).dtype != np.float32 else 2e-2
+    if ts_hint is None or not np.isfinite(ts_hint) or ts_hint <= 0:
+        pos = t[t > 0]
+        ts_hint = float(pos.min())
+    ts_hint = float(ts_hint)
+    probe = t[:: max(1, len(t) // 256)]                              # cheap rejection before the full check
+    for m in range(1, GRID_MAX_DIVISOR + 1):
+        grid = ts_hint / m
+        if tmax / grid >= _cabi.TICK_LIMIT:
+            break
+        if _on_grid(probe, grid, tol) and _on_grid(t, grid, tol):
+            return np.rint(t / grid).astype(np.int64), grid
+    # continuous data: fixed point
+    srt = np.sort(t)[-SLICE_SUM_DATA:]
+    levels = float(_cabi.TICK_LIMIT - 1)
+    while levels > 2 and float(np.sum(np.rint(srt / (tmax / levels)))) >= float(1 << 32):
+        levels = np.floor(levels / 2)
+    grid = tmax / levels
+    return np.rint(t / grid).astype(np.int64), grid
 
 
 def _torch():
@@ -182,6 +231,16 @@ class GibbsEngine:
         if check.ctas_per_sm < per_sm:
             raise _cabi.BrtaError('schedule assumes more co-resident CTAs than the device grants')
         return plan
+
+    @staticmethod
+    def _watchdog_ns(plan, n_data, niter):
+        """Rendezvous watchdog of the launch: a CTA may legitimately wait for a team mate that is still
+        finishing its previous wave, i.e. up to about the whole run.  Ten times a generous estimate of the
+        run (20 cycles per quad and iteration at 1.5 GHz along the schedule's critical path), at least 60 s."""
+        quads = float(np.sum((np.asarray(n_data, dtype=np.int64) + 3) // 4))
+        makespan = quads / max(plan.grid * max(plan.est_efficiency, 1e-3), 1.0) + 400.0 * plan.n_waves
+        est_s = makespan * float(niter) * 20.0 / 1.5e9
+        return int(max(60.0, 10.0 * est_s) * 1e9)
 
     # ---- pack + upload -------------------------------------------------------------------
     def prepare(self, chains, ncomp, niter, thin=100, seed=0, flags=0, inject=None, n_waves=None, shard=None,
@@ -286,6 +345,8 @@ class GibbsEngine:
         b.tick_bytes = ticks.dtype.itemsize
         b.flags = int(flags)
         b.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        b.device = self.device
+        b.watchdog_ns = self._watchdog_ns(plan, n_local, niter)
         b.ticks = up('ticks', ticks.view(np.int16 if tick_dtype == np.uint16 else np.int32))
         b.tick_offset = up('tick_offset', tick_offset)
         if shard is None:                                  # sharded runs keep canonical order, see run_sharded
@@ -325,7 +386,6 @@ class GibbsEngine:
             b.n_shards, b.shard_rank = int(shard['n_shards']), int(shard['rank'])
             b.shard_mailbox = shard['mailbox_table'].data_ptr()
             T['shard_mailbox_table'] = shard['mailbox_table']
-            b.shard_totals = dev_zeros('shard_totals', (_cabi.SHARD_TOTALS_BYTES,), torch.uint8)
 
         inject = inject or {}
         if flags & _cabi.FLAG_INJECT_COEF:
@@ -616,6 +676,105 @@ class GibbsEngine:
                 trace_tk=None if tr_tk is None else tr_tk[r]))
         return res
 
+    # ---- overlapped output path ----------------------------------------
+    STREAM_CHUNK_BYTES = 128 << 20
+    STREAM_RING = 6
+
+    def _ring(self):
+        """Pinned staging buffers, allocated once per engine (page-locking memory is slow: ~0.3 s/GB)."""
+        if getattr(self, '_ring_bufs', None) is None:
+            torch = self.torch
+            self._ring_bufs = [torch.empty(self.STREAM_CHUNK_BYTES, dtype=torch.uint8, pin_memory=True)
+                               for _ in range(self.STREAM_RING)]
+            with torch.cuda.device(self.device):
+                self._copy_stream = torch.cuda.Stream()
+        return self._ring_bufs
+
+    def stream_results(self, db, on_chain, pool, dest=None, keep_on_device=False):
+        """D2H of a launched batch, overlapped with whatever ``on_chain`` does with a finished chain
+        (normally: assign the arrays to the ``Gibbs`` object and write its pickle).
+
+        The dense label buffer (chain r = ``rows * N_r`` contiguous bytes) is copied in chunks through a
+        ring of pinned staging buffers on a copy stream; worker threads of ``pool`` (a
+        ``ThreadPoolExecutor``) scatter each chunk into the per-chain destination arrays ``dest[r]``
+        (``uint8 [rows, N_r]``, allocated here if None) and call ``on_chain(r, ChainResult)`` once the
+        last byte of chain r has landed.  ``keep_on_device``: no label bytes cross PCIe at all;
+        ``ChainResult.indicator`` is then a CUDA tensor view ``[rows, N_r]`` of the resident buffer
+        (SURVEY.md 8 f-1).  Returns the list of futures of the ``on_chain`` calls."""
+        import queue
+        import threading
+        torch = self.torch
+        T = db.tensors
+        R = len(db.n_data)
+        rows = db.rows
+        sizes = np.array([rows * int(n) for n in db.n_data], dtype=np.int64)
+        offs = np.asarray(db.ind_offset, dtype=np.int64)
+        if dest is None and not keep_on_device:
+            dest = [np.empty((rows, int(n)), dtype=np.uint8) for n in db.n_data]
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream().synchronize()                       # the sampler is done
+            status = T['status'].cpu().numpy()
+            mcw = T['mcweights'].cpu().numpy()
+            mcr = T['mcrates'].cpu().numpy()
+
+        def result(r):
+            if keep_on_device:
+                o = int(offs[r])
+                ind = T['indicator'][o:o + int(sizes[r])].view(rows, int(db.n_data[r]))
+            else:
+                ind = dest[r]
+            return ChainResult(mcweights=mcw[r, :rows].copy(), mcrates=mcr[r, :rows].copy(), indicator=ind,
+                               status=int(status[r]))
+
+        if keep_on_device or int(sizes.sum()) == 0:
+            return [pool.submit(on_chain, r, result(r)) for r in range(R)]
+
+        ring = self._ring()
+        free = queue.Queue()                                                # indices of staging buffers not in use
+        for k in range(len(ring)):
+            free.put(k)
+        remaining = sizes.copy()
+        lock = threading.Lock()
+        futures = []
+        total = int(sizes.sum())
+        flat = T['indicator']
+        ends = offs + sizes
+
+        def scatter(slot, a, b, ev):
+            try:
+                ev.synchronize()
+                src = ring[slot].numpy()
+                first = int(np.searchsorted(ends, a, side='right'))
+                done = []
+                for r in range(first, R):
+                    lo, hi = max(a, int(offs[r])), min(b, int(ends[r]))
+                    if lo >= hi:
+                        if int(offs[r]) >= b:
+                            break
+                        continue
+                    np.copyto(dest[r].reshape(-1)[lo - int(offs[r]):hi - int(offs[r])], src[lo - a:hi - a])
+                    with lock:
+                        remaining[r] -= hi - lo
+                        if remaining[r] == 0:
+                            done.append(r)
+            finally:
+                free.put(slot)
+            for r in done:
+                on_chain(r, result(r))
+
+        with torch.cuda.device(self.device):
+            for a in range(0, total, self.STREAM_CHUNK_BYTES):
+                b = min(a + self.STREAM_CHUNK_BYTES, total)
+                slot = free.get()
+                with torch.cuda.stream(self._copy_stream):
+                    ring[slot][:b - a].copy_(flat[a:b], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                futures.append(pool.submit(scatter, slot, a, b, ev))
+        for r in np.nonzero(sizes == 0)[0]:
+            futures.append(pool.submit(on_chain, int(r), result(int(r))))
+        return futures
+
     def run(self, chains, ncomp, niter, thin=100, seed=0, flags=0, inject=None, n_waves=None):
         db = self.prepare(chains, ncomp, niter, thin=thin, seed=seed, flags=flags, inject=inject,
                           n_waves=n_waves)
@@ -623,16 +782,27 @@ class GibbsEngine:
         return self.fetch(db)
 
 
+def shard_bounds(n_data, n_shards):
+    """Quad boundaries of a chain of ``n_data`` data cut into ``n_shards`` contiguous shards of (nearly) equal
+    length; even quad counts keep every shard 16-byte aligned.  Returns n_shards + 1 quad indices."""
+    nq = (int(n_data) + 3) // 4
+    per = -(-nq // int(n_shards))
+    per += per & 1
+    bounds = [min(g * per, nq) for g in range(int(n_shards) + 1)]
+    if bounds[-2] >= nq:
+        raise ValueError('chain too short to shard over that many devices')
+    return bounds
+
+
 def run_sharded(chain, ncomp, niter, devices, thin=100, seed=0, flags=0, inject=None):
     """ONE chain with its residence times sharded over several GPUs of a box (config C4 of
-    BASELINE.json): GPU g sweeps a contiguous range of the data; once per iteration the GPUs
-    exchange their integer (n_k, sum tick_k) through tagged words written into each other's
-    memory over NVLink, inside the persistent kernels -- there is no host round trip and no
-    NCCL call per iteration.  Every GPU then draws the identical posterior update from the same
-    Philox key.  Results are bit-identical to the single-GPU run (Philox is keyed by the global
-    datum index; the statistics are integers).
+    BASELINE.json), all GPUs driven by THIS process: GPU g sweeps a contiguous range of the data; once
+    per iteration the GPUs exchange their integer (n_k, sum tick_k) through tagged words written into
+    each other's memory over NVLink, inside the persistent kernels -- there is no host round trip and
+    no NCCL call per iteration.  Every GPU then draws the identical posterior update from the same
+    Philox key.  Results are bit-identical to the single-GPU run (Philox is keyed by the global datum
+    index; the statistics are integers).  :func:`run_sharded_dist` is the one-process-per-GPU form.
 
-    One host process drives all devices (peer access is enabled between every pair).
     Returns one :class:`ChainResult` for the whole chain."""
     import torch
     devices = [int(d) for d in devices]
@@ -645,13 +815,7 @@ def run_sharded(chain, ncomp, niter, devices, thin=100, seed=0, flags=0, inject=
         for bdev in devices:
             if a != bdev:
                 _cabi.check(lib.brta_enable_peer_access(a, bdev), 'brta_enable_peer_access')
-    n = len(chain.ticks)
-    nq = (n + 3) // 4
-    per = -(-nq // G)
-    per += per & 1                                               # even quad boundaries keep 16-byte alignment
-    bounds = [min(g * per, nq) for g in range(G + 1)]
-    if bounds[-2] >= nq:
-        raise ValueError('chain too short to shard over that many devices')
+    bounds = shard_bounds(len(chain.ticks), G)
     mailboxes = [torch.zeros(_cabi.shard_mailbox_bytes(G), dtype=torch.uint8, device=f'cuda:{d}') for d in devices]
     ptrs = np.array([m.data_ptr() for m in mailboxes], dtype=np.int64)
     batches = []
@@ -677,6 +841,111 @@ def run_sharded(chain, ncomp, niter, devices, thin=100, seed=0, flags=0, inject=
     indicator[:, batches[0].order[0]] = canonical
     return ChainResult(mcweights=first.mcweights, mcrates=first.mcrates, indicator=indicator, status=status,
                        trace_nk=first.trace_nk, trace_tk=first.trace_tk)
+
+
+class ShardedChain:
+    """This rank's part of ONE chain sharded over the ranks of a ``torch.distributed`` group, one
+    process and one GPU per rank (``torchrun``): the one-process-per-GPU form of :func:`run_sharded`.
+
+    Every rank allocates its mailbox with ``brta_shard_mailbox_create`` and maps its peers' through
+    CUDA IPC handles exchanged with ONE ``all_gather`` at set-up; after that the ranks only meet
+    inside the kernels (tagged words over NVLink, SURVEY.md 8e: an allreduce of 2K integers per
+    iteration).  Collective: every rank constructs it with the same chain and parameters.
+
+    ``launch()`` is asynchronous; ``fetch()`` returns this rank's :class:`ChainResult` whose
+    ``indicator`` holds the rank's shard of the data in CANONICAL (ascending-tick) order --
+    columns ``data_begin : data_end`` of the canonical order (``order`` maps back)."""
+
+    def __init__(self, chain, ncomp, niter, thin=100, seed=0, flags=0, group=None, device=None, inject=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if not 1 <= self.world <= _cabi.MAX_SHARDS:
+            raise ValueError(f'1..{_cabi.MAX_SHARDS} ranks')
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.engine = get_engine(self.device)
+        self.lib = _cabi.load()
+        G = self.world
+        own = C.c_void_p()
+        handle = C.create_string_buffer(_cabi.IPC_HANDLE_BYTES)
+        _cabi.check(self.lib.brta_shard_mailbox_create(self.device, G, C.byref(own), handle), 'brta_shard_mailbox_create')
+        self._own = own.value
+        # the only host-side collective: everybody learns everybody's mailbox handle
+        mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8)
+        on_gpu = dist.get_backend(group) == 'nccl'
+        if on_gpu:
+            mine = mine.to(f'cuda:{self.device}')
+        gathered = [torch.empty_like(mine) for _ in range(G)]
+        dist.all_gather(gathered, mine, group=group)
+        self._opened = []
+        ptrs = []
+        for g in range(G):
+            if g == self.rank:
+                ptrs.append(self._own)
+                continue
+            peer = C.c_void_p()
+            raw = bytes(gathered[g].cpu().numpy().tobytes())
+            _cabi.check(self.lib.brta_shard_mailbox_open(self.device, raw, C.byref(peer)), 'brta_shard_mailbox_open')
+            self._opened.append(peer.value)
+            ptrs.append(peer.value)
+        bounds = shard_bounds(len(chain.ticks), G)
+        with torch.cuda.device(self.device):
+            table = torch.from_numpy(np.array(ptrs, dtype=np.int64)).to(f'cuda:{self.device}')
+            shard = dict(rank=self.rank, n_shards=G, quad_begin=bounds[self.rank],
+                         quad_count=bounds[self.rank + 1] - bounds[self.rank], mailbox_table=table)
+            self.db = self.engine.prepare([chain], ncomp, niter, thin=thin, seed=seed, flags=flags, inject=inject,
+                                          shard=shard)
+        self.order = self.db.order[0]
+        self.data_begin = 4 * bounds[self.rank]
+        self.data_end = min(4 * bounds[self.rank + 1], len(chain.ticks))
+        self.niter = int(niter)
+        self._launches = 0
+
+    def launch(self):
+        """Enqueue this rank's kernel.  The G kernels wait for each other on the device, so every rank must
+        call it (a host barrier first keeps a late rank from eating into the watchdog).  The mailbox tags
+        are iteration numbers, so a re-run first zeroes the mailboxes (between two barriers: no rank may
+        still be reading, none may already be writing)."""
+        torch = self.torch
+        torch.cuda.synchronize(self.device)
+        if self._launches:
+            self.dist.barrier(group=self.group)
+            with torch.cuda.device(self.device):
+                _cabi.check(self.lib.brta_shard_mailbox_clear(self.device, C.c_void_p(self._own), self.world,
+                                                              C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                            'brta_shard_mailbox_clear')
+                self.engine.reset(self.db)
+            torch.cuda.synchronize(self.device)
+        self._launches += 1
+        self.dist.barrier(group=self.group)
+        self.engine.launch(self.db)
+
+    def fetch(self):
+        return self.engine.fetch(self.db)[0]
+
+    def close(self):
+        self.torch.cuda.synchronize(self.device)
+        self.dist.barrier(group=self.group)                           # nobody unmaps memory a peer still writes to
+        for p in self._opened:
+            _cabi.check(self.lib.brta_shard_mailbox_close(self.device, C.c_void_p(p)), 'brta_shard_mailbox_close')
+        self._opened = []
+        self.dist.barrier(group=self.group)
+        if self._own is not None:
+            _cabi.check(self.lib.brta_shard_mailbox_destroy(self.device, C.c_void_p(self._own)), 'brta_shard_mailbox_destroy')
+            self._own = None
+
+
+def run_sharded_dist(chain, ncomp, niter, thin=100, seed=0, flags=0, group=None, device=None):
+    """Collective convenience wrapper of :class:`ShardedChain`: run, fetch, close.  Returns
+    (this rank's ChainResult, (data_begin, data_end) of its shard in canonical order, order)."""
+    sc = ShardedChain(chain, ncomp, niter, thin=thin, seed=seed, flags=flags, group=group, device=device)
+    try:
+        sc.launch()
+        res = sc.fetch()
+    finally:
+        sc.close()
+    return res, (sc.data_begin, sc.data_end), sc.order
 
 
 _engines = {}

@@ -16,16 +16,23 @@ Mirrors the public surface of the reference's ``basicrta/gibbs.py`` for the hot 
 The sweep itself (gibbs.py:191-217) is ``brta_gibbs_run_batch`` of the C ABI; there is no
 CPU implementation in this package.  Posterior processing (``cluster``, ``process_gibbs``,
 ``estimate_tau``) stays on the host, plot-free, in :mod:`basicrta_b200.postprocess`.
+
+Output path: the labels of a batch come back in chunks through pinned staging
+buffers while worker threads scatter them into the per-residue arrays and write the pickles; the
+pickle stream names the reference's classes (``basicrta.gibbs.Gibbs``,
+``MDAnalysis.analysis.base.Results``), so a stock basicrta loads it without this package.
 """
 import os
 import pickle
+import struct
 import threading
 import zlib
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
 from . import _cabi
-from .engine import ChainInput, coefficients, get_engine, times_to_ticks
+from .engine import ChainInput, coefficients, get_engine, tick_grid
 from .plan import shard_chains
 from .util import get_s
 
@@ -41,6 +48,21 @@ def _fresh_seed():
 
 def _chain_id(residue, cutoff):
     return zlib.crc32(f'{residue}|{cutoff}'.encode()) & 0xFFFFFFFF
+
+
+class GibbsBatchError(RuntimeError):
+    """Some residues of a batch failed; every other residue was sampled (and saved) normally.
+    ``failures``: list of (residue, exception)."""
+
+    def __init__(self, failures):
+        self.failures = list(failures)
+        lines = '; '.join(f'{res}: {type(e).__name__}: {e}' for res, e in self.failures[:8])
+        more = '' if len(self.failures) <= 8 else f' ... and {len(self.failures) - 8} more'
+        super().__init__(f'{len(self.failures)} residue(s) failed -- {lines}{more}')
+
+
+# attributes that only exist at run time and never enter the pickle
+_TRANSIENT = ('_device_indicator', '_device_batch')
 
 
 class Gibbs(object):
@@ -78,19 +100,25 @@ class Gibbs(object):
     def __getitem__(self, item):
         return getattr(self, item)
 
+    def __getstate__(self):
+        return {k: v for k, v in self.__dict__.items() if k not in _TRANSIENT}
+
     # ---- host preparation (gibbs.py:162-174) ---------------------------------------------
-    def _prepare(self):
+    def _prepare(self, allocate_indicator=True):
         self.t, self.s = get_s(self.times, self.ts)
         rows = (self.niter + 1) // self.g
-        self.indicator = np.zeros((rows, self.times.shape[0]), dtype=np.uint8)
+        # the batch path fills `indicator` from the device and skips this zero-filled allocation
+        self.indicator = np.zeros((rows, self.times.shape[0]), dtype=np.uint8) if allocate_indicator else None
         self.mcweights = np.zeros((rows, self.ncomp))
         self.mcrates = np.zeros((rows, self.ncomp))
         self.whypers = np.ones(self.ncomp) / [self.ncomp]
         self.rhypers = np.ones((self.ncomp, 2)) * [1, 3]
 
     def _chain_input(self):
-        times = np.asarray(self.times, dtype=np.float64)
-        return ChainInput(ticks=times_to_ticks(times, self.ts), ts=float(self.ts),
+        """The chain in device units.  The device grid is NOT ``self.ts`` (the reference's first gap,
+        kept for the pickle) but the coarsest grid all times lie on, see :func:`engine.tick_grid`."""
+        ticks, grid = tick_grid(self.times, self.ts)
+        return ChainInput(ticks=ticks, ts=float(grid),
                           chain_id=_chain_id(self.residue, self.cutoff),
                           whypers=np.asarray(self.whypers, dtype=np.float64),
                           rhypers=np.asarray(self.rhypers, dtype=np.float64))
@@ -99,29 +127,44 @@ class Gibbs(object):
         return f'basicrta-{self.cutoff}/{self.residue}'
 
     # ---- the sampler (gibbs.py:176-219) ---------------------------------------------------
-    def run(self):
-        """Run the sampler on the GPU and pickle the instance, like the reference's ``run``."""
-        self._prepare()
+    def run(self, keep_indicator_on_device=False):
+        """Run the sampler on the GPU and pickle the instance, like the reference's ``run``.
+
+        ``keep_indicator_on_device``: the label rows stay in HBM (``self.indicator`` is None, which the
+        reference's ``cluster`` understands, gibbs.py:259-262); ``process_gibbs(device=...)`` /
+        ``cluster(device=...)`` then reduce them to cluster counts on the GPU and only ``[N, clusters]``
+        integers cross PCIe."""
+        self._prepare(allocate_indicator=False)
         os.makedirs(self._savedir(), exist_ok=True)
-        run_batch([self], device=getattr(self, 'device', None), prepared=True)
-        self.save()
+        try:
+            run_batch([self], device=getattr(self, 'device', None), prepared=True, save=True,
+                      keep_indicator_on_device=keep_indicator_on_device)
+        except GibbsBatchError as e:
+            raise e.failures[0][1] from None
 
     def _sample_indicator(self):
         """Re-draw the labels of every stored (mcweights, mcrates) row without a parameter
         update (gibbs.py:321-334): the sweep kernel in teacher-forced mode, thin = 1."""
         rows = self.mcweights.shape[0]
-        coef = [coefficients(w, r, self.ts) for w, r in zip(self.mcweights, self.mcrates)]
+        ticks, grid = tick_grid(self.times, self.ts)
+        coef = [coefficients(w, r, grid) for w, r in zip(self.mcweights, self.mcrates)]
         eng = get_engine(_pick_device(getattr(self, 'device', None), self.loc))
-        chain = ChainInput(ticks=times_to_ticks(self.times, self.ts), ts=float(self.ts),
-                           chain_id=_chain_id(self.residue, self.cutoff))
+        chain = ChainInput(ticks=ticks, ts=float(grid), chain_id=_chain_id(self.residue, self.cutoff))
         seed = getattr(self, 'seed', None)
         res = eng.run([chain], self.ncomp, rows, thin=1, seed=_fresh_seed() if seed is None else seed,
                       flags=_cabi.FLAG_INJECT_COEF,
                       inject={'coef_c': [np.stack([c for c, _ in coef])],
                               'coef_a': [np.stack([a for _, a in coef])]})[0]
-        _raise_on_status(self.residue, res.status)
+        err = _status_error(self.residue, res.status)
+        if err is not None:
+            raise err
         self.indicator = np.ascontiguousarray(res.indicator[:rows])   # (niter+1)//1 rows are allocated, `rows` filled
         return self.indicator[self.burnin // self.g:]
+
+    def device_indicator(self):
+        """The label rows still resident on the GPU (``run(keep_indicator_on_device=True)``), as a CUDA
+        uint8 tensor ``[rows, N]``, or None."""
+        return getattr(self, '_device_indicator', None)
 
     # ---- persistence (gibbs.py:336-381) ---------------------------------------------------
     def save(self):
@@ -132,7 +175,7 @@ class Gibbs(object):
         if os.path.exists(savedir + filename):
             os.rename(savedir + filename, savedir + filename + '.bak')
         with open(savedir + filename, 'w+b') as f:
-            pickle.dump(self, f)
+            dump_reference_pickle(self, f)
 
     @staticmethod
     def load(file):
@@ -140,7 +183,7 @@ class Gibbs(object):
                 'processed_results', 'ts', 'mcweights', 'mcrates', 't',
                 's', 'cutoff', 'indicator', 'whypers', 'rhypers']
         with open(file, 'r+b') as f:
-            r = pickle.load(f)
+            r = load_reference_pickle(f)
         g = Gibbs()
         for attr in keys:
             try:
@@ -154,9 +197,9 @@ class Gibbs(object):
         return g
 
     # ---- posterior processing: host side, see postprocess.py -------------------------------
-    def cluster(self, method='GaussianMixture', **kwargs):
+    def cluster(self, method='GaussianMixture', device=None, **kwargs):
         from . import postprocess
-        return postprocess.cluster(self, method=method, **kwargs)
+        return postprocess.cluster(self, method=method, device=device, **kwargs)
 
     def process_gibbs(self, save=True, device=None):
         from . import postprocess
@@ -167,11 +210,68 @@ class Gibbs(object):
         return postprocess.estimate_tau(self)
 
 
-def _raise_on_status(residue, status):
+# ---- pickles that a stock basicrta can read -------------------------------------------------------
+# The reference pickles the whole instance (gibbs.py:347) and its loader needs the class importable as
+# ``basicrta.gibbs.Gibbs`` and ``processed_results`` as ``MDAnalysis.analysis.base.Results``
+# (gibbs.py:9, 351-381).  The stream written here names exactly those, whatever this package is called,
+# and writes the big arrays straight from their memory (protocol 5, in band): no intermediate copy, and
+# the file write releases the GIL, so a pool of writer threads scales.
+def _class_aliases():
+    from .results import Results as OwnResults
+    return {Gibbs: ('basicrta.gibbs', 'Gibbs'), OwnResults: ('MDAnalysis.analysis.base', 'Results')}
+
+
+class _RefPickler(pickle._Pickler):
+    dispatch = pickle._Pickler.dispatch.copy()
+
+    def __init__(self, file):
+        super().__init__(file, protocol=5)
+        self._aliases = _class_aliases()
+
+    def save_global(self, obj, name=None):
+        alias = self._aliases.get(obj) if isinstance(obj, type) else None
+        if alias is None:
+            return super().save_global(obj, name)
+        self.save(alias[0])
+        self.save(alias[1])
+        self.write(pickle.STACK_GLOBAL)
+        self.memoize(obj)
+
+    def _save_buffer_in_band(self, obj):
+        # a buffer is written once and nothing else refers to it, so it needs no memo entry
+        with obj.raw() as m:
+            header = (pickle.BINBYTES8 if m.readonly else pickle.BYTEARRAY8) + struct.pack('<Q', m.nbytes)
+            if m.nbytes >= self.framer._FRAME_SIZE_TARGET:
+                self._write_large_bytes(header, m)          # straight from the array's memory
+            else:
+                self.write(header + m.tobytes())
+
+    dispatch[pickle.PickleBuffer] = _save_buffer_in_band
+
+
+class _RefUnpickler(pickle.Unpickler):
+    def find_class(self, module, name):
+        if (module, name) == ('basicrta.gibbs', 'Gibbs'):
+            return Gibbs
+        if (module, name) == ('MDAnalysis.analysis.base', 'Results'):
+            return Results
+        return super().find_class(module, name)
+
+
+def dump_reference_pickle(obj, f):
+    _RefPickler(f).dump(obj)
+
+
+def load_reference_pickle(f):
+    return _RefUnpickler(f).load()
+
+
+def _status_error(residue, status):
     if status & _cabi.STATUS_TIMEOUT:
-        raise _cabi.BrtaError(f'residue {residue}: team rendezvous timed out on the device (status {status})')
+        return _cabi.BrtaError(f'residue {residue}: team rendezvous timed out on the device (status {status})')
     if status != _cabi.STATUS_OK:
-        raise FloatingPointError(f'residue {residue}: sampler saw a non-finite likelihood (status {status})')
+        return FloatingPointError(f'residue {residue}: sampler saw a non-finite likelihood (status {status})')
+    return None
 
 
 def _device_count():
@@ -185,31 +285,82 @@ def _pick_device(device, loc=0):
     return int(device) if device is not None else int(loc) % _device_count()
 
 
-def run_batch(gibbs_list, device=None, seed=None, prepared=False, engine=None):
+WRITER_THREADS = 8
+
+
+def run_batch(gibbs_list, device=None, seed=None, prepared=False, engine=None, save=False,
+              keep_indicator_on_device=False, pool=None, progress=None):
     """Run many residues' chains in ONE launch on one GPU and fill their output arrays.
 
     All members must share ``ncomp``, ``niter`` and ``g`` (``ParallelGibbs`` guarantees it,
     gibbs.py:73-75).  Hyper-parameters and ``g`` are read here, i.e. at run time.
+
+    Residues fail one by one, as in the reference's pool (one worker's exception does not stop the
+    others, gibbs.py:80-88): a residue whose input is unusable is left out of the launch, a chain that
+    ends with a non-zero device status is not assigned; all others are assigned (and, with ``save``,
+    pickled by a pool of writer threads while the rest of the labels are still coming back over PCIe).
+    Failures are reported together at the end as :class:`GibbsBatchError`.
     """
     if not gibbs_list:
         return
     first = gibbs_list[0]
     key = (first.ncomp, first.niter, first.g)
+    failures = []
+    members, inputs = [], []
     for gb in gibbs_list:
         if (gb.ncomp, gb.niter, gb.g) != key:
             raise ValueError('a batch needs one (ncomp, niter, g)')
-        if not prepared:
-            gb._prepare()
-    eng = engine if engine is not None else get_engine(_pick_device(device, first.loc))
-    if seed is None:
-        seed = getattr(first, 'seed', None)
-    if seed is None:
-        seed = _fresh_seed()
-    res = eng.run([gb._chain_input() for gb in gibbs_list], first.ncomp, first.niter,
-                  thin=first.g, seed=seed)
-    for gb, r in zip(gibbs_list, res):
-        _raise_on_status(gb.residue, r.status)
-        gb.mcweights, gb.mcrates, gb.indicator = r.mcweights, r.mcrates, r.indicator
+        try:
+            if not prepared:
+                gb._prepare(allocate_indicator=False)
+            inputs.append(gb._chain_input())
+            members.append(gb)
+        except (ValueError, TypeError, FloatingPointError, MemoryError) as e:
+            failures.append((gb.residue, e))
+    if members:
+        eng = engine if engine is not None else get_engine(_pick_device(device, first.loc))
+        if seed is None:
+            seed = getattr(first, 'seed', None)
+        if seed is None:
+            seed = _fresh_seed()
+        db = eng.prepare(inputs, first.ncomp, first.niter, thin=first.g, seed=seed)
+        if progress is not None:
+            progress(0, first.niter)
+        eng.launch(db)
+        lock = threading.Lock()
+
+        def on_chain(r, res):
+            gb = members[r]
+            err = _status_error(gb.residue, res.status)
+            if err is None:
+                try:
+                    gb.mcweights, gb.mcrates = res.mcweights, res.mcrates
+                    if keep_indicator_on_device:
+                        gb.indicator, gb._device_indicator, gb._device_batch = None, res.indicator, db
+                    else:
+                        gb.indicator = res.indicator
+                        gb.__dict__.pop('_device_indicator', None)
+                    if save:
+                        os.makedirs(gb._savedir(), exist_ok=True)
+                        gb.save()
+                except Exception as e:                      # e.g. disk full: this residue only
+                    err = e
+            if err is not None:
+                with lock:
+                    failures.append((gb.residue, err))
+
+        own_pool = pool is None
+        pool = ThreadPoolExecutor(max_workers=WRITER_THREADS) if own_pool else pool
+        try:
+            for fut in eng.stream_results(db, on_chain, pool, keep_on_device=keep_indicator_on_device):
+                fut.result()
+        finally:
+            if own_pool:
+                pool.shutdown(wait=True)
+        if progress is not None:
+            progress(first.niter, first.niter)
+    if failures:
+        raise GibbsBatchError(failures)
 
 
 class ParallelGibbs(object):
@@ -244,53 +395,66 @@ class ParallelGibbs(object):
             return [f'X{int(r)}' for r in resids]
 
     def _load(self, run_resids):
-        with open(self.contacts, 'r+b') as f:
-            contacts = pickle.load(f)
-        protids = np.unique(contacts[:, 0])
-        if run_resids is None or (np.ndim(run_resids) == 0 and not run_resids) or \
-                (np.ndim(run_resids) > 0 and len(run_resids) == 0):
-            run_resids = protids
-        if not isinstance(run_resids, (list, np.ndarray)):
-            run_resids = [run_resids]
-        run_resids = np.asarray(run_resids)
-        # one stable sort groups all residues' durations (column 3) instead of one boolean
-        # mask per residue (gibbs.py:68-69 is O(R*M))
-        order = np.argsort(contacts[:, 0], kind='stable')
-        col0 = np.asarray(contacts[:, 0])[order]
-        dur = np.asarray(contacts[:, 3], dtype=np.float64)[order]
-        lo = np.searchsorted(col0, run_resids, side='left')
-        hi = np.searchsorted(col0, run_resids, side='right')
-        times = [dur[a:b].copy() for a, b in zip(lo, hi)]
-        return run_resids, self._residue_names(contacts, run_resids), times
+        return load_contacts(self.contacts, run_resids, self._residue_names)
 
-    def run(self, run_resids=None):
+    def run(self, run_resids=None, skip_existing=False):
+        """``skip_existing``: the reference's rerun rule (scripts/get_rerun_residues.py:22-28) -- a residue
+        whose ``gibbs_{niter}.pkl`` already exists is not sampled again."""
         resids, names, times = self._load(run_resids)
         n_gpu = max(1, min(int(self.nproc), _device_count()))
         gibbs = [Gibbs(t, name, i % n_gpu, ncomp=self.ncomp, niter=self.niter, cutoff=self.cutoff)
                  for i, (name, t) in enumerate(zip(names, times)) if len(t) > 0]
+        if skip_existing:
+            gibbs = [g for g in gibbs if not os.path.exists(f'{g._savedir()}/gibbs_{g.niter}.pkl')]
         dispatch(gibbs, n_gpu)
         return gibbs
 
 
-def dispatch(gibbs_list, n_gpu, seed=None, save=True):
+def load_contacts(path, run_resids=None, namer=None):
+    """Per-residue residence times of one ``contacts_{cutoff}.pkl`` (column 0 = protein resid, column 3 =
+    duration in ns, contacts.py:227-229): one stable sort groups all residues' durations instead of one
+    boolean mask per residue (gibbs.py:68-69 is O(R*M)).  Returns (resids, names, list of times)."""
+    with open(path, 'r+b') as f:
+        contacts = pickle.load(f)
+    protids = np.unique(contacts[:, 0])
+    if run_resids is None or (np.ndim(run_resids) == 0 and not run_resids) or \
+            (np.ndim(run_resids) > 0 and len(run_resids) == 0):
+        run_resids = protids
+    if not isinstance(run_resids, (list, np.ndarray)):
+        run_resids = [run_resids]
+    run_resids = np.asarray(run_resids)
+    order = np.argsort(contacts[:, 0], kind='stable')
+    col0 = np.asarray(contacts[:, 0])[order]
+    dur = np.asarray(contacts[:, 3], dtype=np.float64)[order]
+    lo = np.searchsorted(col0, run_resids, side='left')
+    hi = np.searchsorted(col0, run_resids, side='right')
+    times = [dur[a:b].copy() for a, b in zip(lo, hi)]
+    namer = namer or ParallelGibbs._residue_names
+    return run_resids, namer(contacts, run_resids), times
+
+
+def dispatch(gibbs_list, n_gpu, seed=None, save=True, keep_indicator_on_device=False, progress=None):
     """Shard residues over GPUs (one host thread per GPU, one launch per GPU) and write the
-    reference's per-residue pickles."""
+    reference's per-residue pickles.  ``gibbs_list`` may mix batches -- residues of several contact
+    cutoffs (five ``contacts_{cutoff}.pkl`` -> one launch per GPU), as long as
+    they share (ncomp, niter, g).  Failed residues are collected over all GPUs and raised together as
+    :class:`GibbsBatchError` after every other residue has been written."""
     if not gibbs_list:
         return
     shards = shard_chains([len(g.times) for g in gibbs_list], n_gpu)
-    errors = []
+    failures, errors = [], []
     seed = _fresh_seed() if seed is None else seed
+    pool = ThreadPoolExecutor(max_workers=WRITER_THREADS * max(1, min(n_gpu, 2)))
 
     def work(dev, idx):
         try:
             members = [gibbs_list[i] for i in idx]
             for gb in members:
                 gb.loc = dev
-            run_batch(members, device=dev, seed=seed)
-            if save:
-                for gb in members:
-                    os.makedirs(gb._savedir(), exist_ok=True)
-                    gb.save()
+            run_batch(members, device=dev, seed=seed, save=save, pool=pool,
+                      keep_indicator_on_device=keep_indicator_on_device, progress=progress)
+        except GibbsBatchError as e:
+            failures.extend(e.failures)
         except BaseException as e:                     # surfaced to the caller below
             errors.append(e)
 
@@ -299,17 +463,50 @@ def dispatch(gibbs_list, n_gpu, seed=None, save=True):
         t.start()
     for t in threads:
         t.join()
+    pool.shutdown(wait=True)
     if errors:
         raise errors[0]
+    if failures:
+        raise GibbsBatchError(failures)
+
+
+class MultiCutoffGibbs(object):
+    """The multi-cutoff ensemble (BASELINE.json config 3): the same protein at several contact cutoffs,
+    i.e. several ``contacts_{cutoff}.pkl`` files of ``contacts.ProcessContacts`` (contacts.py:181-191).
+    The reference runs ``python -m basicrta.gibbs --contacts ...`` once per file; here the residues of
+    ALL files go to the GPUs as one batch per GPU (2 000 chains for 400 residues x 5 cutoffs), and every
+    residue is written to its own ``basicrta-{cutoff}/{residue}/`` as before."""
+
+    def __init__(self, contact_files, nproc=1, ncomp=15, niter=110000):
+        self.members = [ParallelGibbs(c, nproc=nproc, ncomp=ncomp, niter=niter) for c in contact_files]
+        self.nproc, self.ncomp, self.niter = nproc, ncomp, niter
+
+    def run(self, run_resids=None, skip_existing=False):
+        n_gpu = max(1, min(int(self.nproc), _device_count()))
+        gibbs = []
+        for pg in self.members:
+            resids, names, times = pg._load(run_resids)
+            gibbs += [Gibbs(t, name, 0, ncomp=self.ncomp, niter=self.niter, cutoff=pg.cutoff)
+                      for name, t in zip(names, times) if len(t) > 0]
+        if skip_existing:
+            gibbs = [g for g in gibbs if not os.path.exists(f'{g._savedir()}/gibbs_{g.niter}.pkl')]
+        dispatch(gibbs, n_gpu)
+        return gibbs
 
 
 if __name__ == '__main__':                             # gibbs.py:781-795
     import argparse
     parser = argparse.ArgumentParser()
-    parser.add_argument('--contacts')
+    parser.add_argument('--contacts', nargs='+')
     parser.add_argument('--resid', type=int, default=None)
     parser.add_argument('--nproc', type=int, default=1)
     parser.add_argument('--niter', type=int, default=110000)
     parser.add_argument('--ncomp', type=int, default=15)
+    parser.add_argument('--skip-existing', action='store_true')
     args = parser.parse_args()
-    ParallelGibbs(args.contacts, nproc=args.nproc, ncomp=args.ncomp, niter=args.niter).run(run_resids=args.resid)
+    if len(args.contacts) == 1:
+        ParallelGibbs(args.contacts[0], nproc=args.nproc, ncomp=args.ncomp, niter=args.niter).run(
+            run_resids=args.resid, skip_existing=args.skip_existing)
+    else:
+        MultiCutoffGibbs(args.contacts, nproc=args.nproc, ncomp=args.ncomp, niter=args.niter).run(
+            run_resids=args.resid, skip_existing=args.skip_existing)

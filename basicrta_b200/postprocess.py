@@ -47,7 +47,13 @@ def cluster(gibbs, method='GaussianMixture', device=None, **kwargs):
     model.fit(np.log(train))
     labels = model.predict(np.log(data))
 
-    indicator = gibbs.indicator[burn:] if gibbs.indicator is not None else gibbs._sample_indicator()
+    resident = getattr(gibbs, '_device_indicator', None)     # Gibbs.run(keep_indicator_on_device=True)
+    if gibbs.indicator is not None:
+        indicator = gibbs.indicator[burn:]
+    elif resident is not None:                               # reduce on the GPU that holds the labels
+        indicator, device = resident[burn:], resident.device.index
+    else:
+        indicator = gibbs._sample_indicator()
     pind = pindicator_counts_host(indicator, rows, comps, labels, lmode, gibbs.ncomp, device).astype(np.float64)
     with np.errstate(invalid='ignore', divide='ignore'):
         pind = (pind.T / pind.sum(axis=1)).T
@@ -59,7 +65,8 @@ def cluster(gibbs, method='GaussianMixture', device=None, **kwargs):
 def pindicator_counts_host(indicator, rows, comps, labels, n_clusters, ncomp, device=None):
     """counts[i, c] = number of retained (row, component) pairs with mixture label c whose component
     labels datum i in that row (gibbs.py:264-268).  NumPy, or the GPU kernel if ``device`` is given."""
-    ncomp = max(int(ncomp), int(indicator.max(initial=0)) + 1)
+    if isinstance(indicator, np.ndarray):
+        ncomp = max(int(ncomp), int(indicator.max(initial=0)) + 1)
     lut = np.full((indicator.shape[0], ncomp), -1, dtype=np.int8)
     lut[rows, comps] = labels
     if device is not None:

@@ -26,9 +26,37 @@ def make_surv(ahist):
     return t, 1 - y
 
 
+DENSE_BINS_MAX = 1 << 22
+
+
 def get_s(x, ts):
-    """``t, s`` stored in the Gibbs pickle (basicrta/util.py:116-120); not used by the sampler."""
-    return make_surv(np.histogram(x, bins=get_bins(x, ts)))
+    """``t, s`` stored in the Gibbs pickle (basicrta/util.py:116-120); not used by the sampler.
+
+    The reference histograms over ``int(x.max() // ts) + 2`` edges ``k * ts`` and keeps the non-empty
+    bins (util.py:611-620, 653-660) -- a billion bins (43 s, 8.6 GB) for continuous times whose
+    first gap is tiny.  Beyond DENSE_BINS_MAX edges the same ``t, s`` are computed
+    from the occupied bins only: bit-identical edges (``float64(k) * ts`` as ``np.arange(...) * ts``
+    gives), same half-open bins with a closed last one."""
+    x = np.asarray(x) if isinstance(x, list) else x
+    if not isinstance(x, np.ndarray):
+        raise TypeError('Input should be a list or array')
+    n_edges = int(x.max() // ts) + 2
+    if n_edges <= DENSE_BINS_MAX:
+        return make_surv(np.histogram(x, bins=get_bins(x, ts)))
+    ts = np.float64(ts)
+    xs = np.sort(np.asarray(x, dtype=np.float64))
+    k = np.floor(xs / ts).astype(np.int64)                    # candidate: edge k*ts <= x, fixed up below
+    for _ in range(3):
+        k = np.where(k.astype(np.float64) * ts > xs, k - 1, k)
+        k = np.where((k + 1).astype(np.float64) * ts <= xs, k + 1, k)
+    last = n_edges                                             # edges are k = 1 .. n_edges; the last bin is closed
+    k = np.where(k >= last, last - 1, k)
+    k = k[k >= 1]                                              # below the first edge: not counted
+    occupied, counts = np.unique(k, return_counts=True)
+    t = np.insert(occupied.astype(np.float64) * ts, 0, 0)
+    y = np.insert(np.cumsum(counts), 0, 0)
+    y = y / y[-1]
+    return t, 1 - y
 
 
 def confidence_interval(data, percentage=95):

@@ -64,6 +64,16 @@ def residue_times(r, seed_offset=0, n_scale=1.0):
     return ticks
 
 
+def c5_residue_times(r):
+    """Residue r of the stress configuration C5: seed 5000+r, N = 20 000, five true
+    components with rates over four decades; run with ncomp = 30."""
+    rng = np.random.default_rng(5000 + r)
+    rates = np.array([10, 1, 0.1, 0.01, 0.001])
+    comp = rng.choice(5, size=20000, p=[0.6, 0.25, 0.1, 0.04, 0.01])
+    x = rng.exponential(1.0 / rates[comp])
+    return np.maximum(np.ceil(x / TS), 1.0).astype(np.int64)
+
+
 def workload(indices):
     return [residue_times(r) for r in indices]
 

@@ -12,8 +12,8 @@
  *   - plain C: pointers and sizes only, no C++/torch types;
  *   - every pointer inside brta_batch is a DEVICE pointer owned by the caller;
  *   - calls are asynchronous on the given CUDA stream (a cudaStream_t passed as
- *     void*); the library allocates nothing and keeps no mutable global state apart
- *     from a per-thread error string;
+ *     void*); the library allocates nothing (brta_shard_mailbox_create excepted) and keeps
+ *     no mutable global state apart from a per-thread error string;
  *   - return value: 0 = ok, < 0 = argument error (BRTA_E_*), > 0 = cudaError_t;
  *   - nothing throws across the boundary; there is no CPU fallback.
  */
@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BRTA_ABI_VERSION 3
+#define BRTA_ABI_VERSION 4
 
 /* compile-time geometry of the sampler kernel */
 #ifndef BRTA_THREADS
@@ -42,8 +42,8 @@ extern "C" {
 
 /* cross-GPU exchange of a sharded chain: 2 parities x G sources x 32 components x 32 B */
 #define BRTA_SHARD_MAILBOX_BYTES(g) (2 * (g) * 32 * 32)
-#define BRTA_SHARD_TOTALS_BYTES     (3 * 32 * 16 + 128)
 #define BRTA_MAX_SHARDS 16
+#define BRTA_IPC_HANDLE_BYTES 64    /* sizeof(cudaIpcMemHandle_t) */
 
 /* brta_batch.flags */
 #define BRTA_FLAG_EXACT        1u   /* IEEE-only arithmetic (bit-exact vs oracle/gibbs_oracle.py) */
@@ -170,12 +170,15 @@ typedef struct brta_batch {
      * sweeps a contiguous range of the chain's quads (tasks carry GLOBAL quad indices; tick_offset /
      * ind_offset are shifted by the caller so that global indices address the local shard) and the GPUs
      * exchange (n_k, sum tick_k) once per iteration through tagged words written into each other's
-     * memory over NVLink (peer access enabled by the caller, see brta_enable_peer_access). */
+     * memory over NVLink: the CTA of a GPU that completes its GPU's totals stores them into EVERY GPU's
+     * mailbox, and every CTA reads all G shards' totals from its own GPU's mailbox.  The mailboxes are
+     * peer-mapped by the caller: one process driving all GPUs (brta_enable_peer_access) or one process
+     * per GPU (brta_shard_mailbox_create / _open: CUDA IPC).  The G launches must be able to run
+     * concurrently; iteration numbers (the tags) must not repeat on a mailbox without zeroing it. */
     int32_t          n_shards;     /* G; 0 or 1 = not sharded                             */
     int32_t          shard_rank;   /* this GPU's position 0..G-1                          */
-    void* const*     shard_mailbox;/* device array of G pointers: mailbox of every GPU, each
-                                      BRTA_SHARD_MAILBOX_BYTES(G) bytes, zeroed               */
-    void*            shard_totals; /* local, BRTA_SHARD_TOTALS_BYTES bytes, zeroed            */
+    void* const*     shard_mailbox;/* device array of G pointers: mailbox of every GPU as mapped into
+                                      this process, each BRTA_SHARD_MAILBOX_BYTES(G) bytes, zeroed  */
 
     void*            exchange;     /* zeroed by the caller; chain r owns BRTA_EXCH_BYTES(team_size)
                                       bytes at exch_offset[r]                             */
@@ -196,6 +199,15 @@ typedef struct brta_batch {
     int32_t          iter_end;     /* last iteration of this launch, <= niter; 0 = niter  */
     float*           final_c;      /* [R,K] may be NULL: coefficients after iteration iter_end, */
     float*           final_a;      /* [R,K] the (init_c, init_a) of the next launch             */
+
+    /* rendezvous watchdog: a wait for team mates (or peer GPUs) longer than this many nanoseconds of
+     * the device's global timer ends the chain with BRTA_STATUS_TIMEOUT instead of hanging the GPU.
+     * Legitimate waits are as long as a team mate needs to finish its previous wave, so the host
+     * scales it from the schedule (engine.py); 0 = 60 s. */
+    uint64_t         watchdog_ns;
+    int32_t          device;       /* CUDA ordinal the pointers live on; the call runs there and restores
+                                      the caller's current device.  -1 = the current device */
+    int32_t          reserved0;
 } brta_batch;
 
 /* Device capabilities.  Python side: Gibbs.run needs it to size the schedule. */
@@ -238,6 +250,24 @@ int brta_mufu_probe(float* sink_dev, int blocks, int iters, void* stream);
 int brta_pindicator_counts(const uint8_t* indicator, int64_t row_stride, int32_t n_rows, int32_t n_data,
                            const int8_t* cluster_of, int32_t ncomp, int32_t n_clusters,
                            int32_t* counts, void* stream);
+
+/* Test hook for the posterior update (gibbs.py:210-211 calls numpy's Generator.dirichlet / .gamma):
+ * out[i] = log2 of a Gamma(shapes[i % n_shapes], 1) variate drawn by the sampler's own device
+ * functions (Marsaglia-Tsang trials on the Philox stream (trial, i, chain, purpose), first accepted
+ * trial, shape < 1 boost in log2 space).  All pointers are device pointers. */
+int brta_gamma_fill(float* out_dev, int64_t n, const float* shapes_dev, int n_shapes, uint32_t chain,
+                    uint32_t purpose, uint64_t seed, void* stream);
+
+/* Mailbox of one GPU of a sharded chain when every GPU is driven by its OWN process (torchrun: one
+ * rank per GPU).  create: cudaMalloc + zero BRTA_SHARD_MAILBOX_BYTES(n_shards) on `device` and export
+ * a CUDA IPC handle (BRTA_IPC_HANDLE_BYTES bytes, to be sent to the peers by any host transport);
+ * open: map a peer's mailbox into this process (peer access is enabled lazily); close / destroy undo
+ * them.  These are the only calls of the library that own device memory. */
+int brta_shard_mailbox_create(int device, int n_shards, void** dev_ptr, unsigned char* handle64);
+int brta_shard_mailbox_open(int device, const unsigned char* handle64, void** dev_ptr);
+int brta_shard_mailbox_clear(int device, void* dev_ptr, int n_shards, void* stream);   /* zero it: before re-running */
+int brta_shard_mailbox_close(int device, void* dev_ptr);
+int brta_shard_mailbox_destroy(int device, void* dev_ptr);
 
 /* Last error message of the calling thread ("" if none). */
 const char* brta_last_error(void);

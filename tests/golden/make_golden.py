@@ -20,6 +20,19 @@ Outputs (committed):
     reference for niter=110000 under 4 seeds: the thinned ``mcweights`` / ``mcrates``
     samples (float32).  This is the statistical truth the CUDA sampler's free-running
     chains are compared with (2 % on posterior means, KS p > 0.01).
+
+``ref_c2_posterior.npz`` / ``ref_c5_posterior.npz``
+    The same for residues of the headline configuration C2 (``bench.residue_times(r)`` for the
+    residues in ``C2_RESIDUES``: N ~ 1e4, K = 15, 2 / 3 / 4 true components) and of the stress
+    configuration C5 (``bench.c5_residue_times(r)``: N = 2e4, K = 30, five components over four
+    decades), 110 000 iterations of the unmodified reference under two seeds each, plus the END of
+    the reference's pipeline per run: ``Gibbs.cluster(n_init=117, n_components=lmode)``
+    (gibbs.py:221-273, unmodified), the label sort of ``util.mixture_and_plot``
+    (util.py:738-756, restated here because the function is ~450 lines of matplotlib),
+    ``Gibbs._estimate_params`` and ``Gibbs.estimate_tau`` (gibbs.py:667-715, unmodified):
+    cluster count, [CI low, tau, CI high], the slowest cluster's tau samples summarised.
+    A reference run that dies with NumPy's ``ValueError`` (0/0 responsibilities,
+    gibbs.py:196-200) is recorded as ``failed`` with the message.
 """
 import os
 import sys
@@ -95,9 +108,92 @@ def make_c1():
     print('wrote ref_c1_posterior.npz')
 
 
+C2_RESIDUES = [22, 4, 249, 329]          # the smallest N with 3 / 2 / 4 / 3 true components
+C5_RESIDUES = [0, 1]
+POSTERIOR_SEEDS = [11, 22]
+
+
+def _label_sort(G):
+    """util.py:738-756 without the figures: clusters ordered by mean rate, fastest first, noise
+    clusters (no datum assigned with probability >= _noise_cutoff) last."""
+    burn = G.burnin // G.g
+    weights, rates = G.mcweights[burn:], G.mcrates[burn:]
+    arates = rates[np.where(weights > 10 / len(G.times))]
+    all_labels = G.processed_results.labels
+    uniq = np.unique(all_labels)
+    imaxs = G.processed_results.indicator.max(axis=0)
+    noise = np.where(imaxs < G._noise_cutoff)[0]
+    means = np.array([arates[all_labels == i].mean() for i in uniq])
+    vsorts = means[np.delete(uniq, noise)].argsort()[::-1]
+    nsorts = means[noise].argsort()[::-1]
+    presorts = np.concatenate([np.delete(uniq, noise)[vsorts], noise[nsorts]]).astype(int)
+    sorts = np.array([np.where(presorts == i)[0][0] for i in uniq])
+    return sorts[all_labels], presorts
+
+
+def _reference_pipeline_end(G):
+    """process_gibbs (gibbs.py:275-308) with mixture_and_plot replaced by its label sort."""
+    from scipy import stats
+    wcutoff = 10 / len(G.times)
+    burn = G.burnin // G.g
+    inds = np.where(G.mcweights[burn:] > wcutoff)
+    weights, rates = G.mcweights[burn:], G.mcrates[burn:]
+    lens = [len(row[row > wcutoff]) for row in weights]
+    lmode = stats.mode(lens).mode
+    G.cluster(n_init=117, n_components=lmode)
+    labels, presorts = _label_sort(G)
+    pr = G.processed_results
+    pr.labels = labels
+    pr.indicator = pr.indicator[:, presorts]
+    pr.weights, pr.rates, pr.ncomp = weights[inds], rates[inds], int(lmode)
+    G._estimate_params()
+    tau = G.estimate_tau()
+    imaxs = pr.indicator.max(axis=0)
+    noise = np.where(imaxs < G._noise_cutoff)[0]
+    valid = np.delete(np.unique(pr.labels), noise)
+    index = pr.parameters[valid, 1].argmin()
+    taus = 1 / pr.rates[pr.labels == index]
+    return dict(ncomp=int(lmode), n_noise=int(len(noise)), tau=np.array(tau, dtype=np.float64),
+                parameters=pr.parameters, tau_median=float(np.median(taus)), tau_mean=float(taus.mean()),
+                tau_binwidth=float((taus.max() - taus.min()) / 15), n_tau=int(len(taus)))
+
+
+def _posterior_worker(job):
+    kind, r, rng_seed = job
+    import bench
+    if kind == 'c2':
+        ticks, ncomp = bench.residue_times(r), 15
+    else:
+        ticks, ncomp = bench.c5_residue_times(r), 30
+    times = ticks * bench.TS
+    try:
+        G = _run_reference(times, ncomp, 110000, 100, rng_seed, residue=f'{kind}r{r}s{rng_seed}')
+    except ValueError as e:                               # 0/0 responsibilities -> NumPy raises (SURVEY a4)
+        return job, dict(failed=str(e))
+    end = _reference_pipeline_end(G)
+    end.update(mcweights=G.mcweights.astype(np.float32), mcrates=G.mcrates.astype(np.float32), n=len(times))
+    return job, end
+
+
+def make_posteriors(kind, residues, nproc=6):
+    jobs = [(kind, r, s) for r in residues for s in POSTERIOR_SEEDS]
+    with Pool(min(nproc, len(jobs))) as p:
+        res = p.map(_posterior_worker, jobs, chunksize=1)
+    out = {'residues': np.array(residues), 'seeds': np.array(POSTERIOR_SEEDS)}
+    for (_, r, s), d in res:
+        for k, v in d.items():
+            out[f'r{r}/s{s}/{k}'] = np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, f'ref_{kind}_posterior.npz'), **out)
+    print(f'wrote ref_{kind}_posterior.npz', len(out), 'arrays')
+
+
 if __name__ == '__main__':
     what = sys.argv[1] if len(sys.argv) > 1 else 'all'
     if what in ('all', 'small'):
         make_replay()
     if what in ('all', 'c1'):
         make_c1()
+    if what in ('all', 'c2'):
+        make_posteriors('c2', C2_RESIDUES)
+    if what in ('all', 'c5'):
+        make_posteriors('c5', C5_RESIDUES)

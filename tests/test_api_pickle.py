@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from basicrta_b200 import postprocess
-from basicrta_b200.gibbs import Gibbs, ParallelGibbs
+from basicrta_b200.gibbs import Gibbs, ParallelGibbs, load_reference_pickle
 from basicrta_b200.cluster import ProcessCluster
 from oracle import gibbs_oracle as O
 
@@ -51,9 +51,70 @@ def test_save_load_roundtrip_and_bak_rotation(tmp_path, monkeypatch):
     for attr in ('times', 'mcweights', 'mcrates', 'indicator', 't', 's', 'whypers', 'rhypers'):
         assert np.array_equal(getattr(back, attr), getattr(gb, attr)), attr
     assert (back.residue, back.ncomp, back.niter, back.g, back.burnin, back.cutoff) == ('W313', 4, 3000, 10, 500, 7.0)
-    raw = pickle.load(open('basicrta-7.0/W313/gibbs_3000.pkl', 'rb'))
-    assert raw.indicator.dtype == np.uint8 and raw.indicator.flags['C_CONTIGUOUS']
+    raw = load_reference_pickle(open('basicrta-7.0/W313/gibbs_3000.pkl', 'rb'))
+    assert raw.indicator.dtype == np.uint8 and raw.indicator.flags['C_CONTIGUOUS'] and raw.indicator.flags.writeable
     assert raw.mcweights.dtype == np.float64 and raw.mcweights.shape == (300, 4)
+
+
+def test_pickle_stream_names_the_reference_classes(tmp_path, monkeypatch):
+    """the pickle must import as ``basicrta.gibbs.Gibbs`` (and its ``processed_results`` as
+    ``MDAnalysis.analysis.base.Results``) so that a stock basicrta -- cluster.ProcessProtein,
+    cluster.py:44-46 -- loads it on a machine that has never seen this package."""
+    import io
+    import pickletools
+    import sys
+    monkeypatch.chdir(tmp_path)
+    gb = _filled_gibbs()
+    gb._device_indicator = object()                          # run-time handle: must not be pickled
+    os.makedirs('basicrta-7.0/W313')
+    gb.save()
+    raw = open('basicrta-7.0/W313/gibbs_3000.pkl', 'rb').read()
+    strings = {a for op, a, _ in pickletools.genops(io.BytesIO(raw)) if op.name in ('SHORT_BINUNICODE', 'BINUNICODE')}
+    assert 'basicrta.gibbs' in strings and 'MDAnalysis.analysis.base' in strings
+    assert not any('basicrta_b200' in str(x) for x in strings) and '_device_indicator' not in strings
+    # a foreign environment: modules of those names that know nothing about basicrta_b200
+    import types
+
+    class ForeignGibbs:
+        def __getitem__(self, k):
+            return getattr(self, k)
+
+    class ForeignResults:
+        def __setstate__(self, state):
+            self.data = state
+
+    saved = {k: sys.modules.get(k) for k in ('basicrta', 'basicrta.gibbs', 'MDAnalysis', 'MDAnalysis.analysis',
+                                             'MDAnalysis.analysis.base')}
+    try:
+        for name in saved:
+            sys.modules[name] = types.ModuleType(name)
+        sys.modules['basicrta.gibbs'].Gibbs = ForeignGibbs
+        sys.modules['MDAnalysis.analysis.base'].Results = ForeignResults
+        obj = pickle.loads(raw)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    assert type(obj) is ForeignGibbs and type(obj.processed_results) is ForeignResults
+    assert obj.processed_results.data == {} and np.array_equal(obj['indicator'], gb.indicator)
+    assert obj.niter == 3000 and obj.residue == 'W313'
+
+
+def test_results_stand_in_behaves_like_the_mdanalysis_class():
+    from basicrta_b200.results import Results
+    r = Results()
+    r.labels = np.arange(3)
+    r['ncomp'] = 2
+    assert r.ncomp == 2 and r['labels'][2] == 2 and set(r.keys()) == {'labels', 'ncomp'}
+    with pytest.raises(AttributeError):
+        r.missing
+    del r.ncomp
+    assert 'ncomp' not in r
+    back = pickle.loads(pickle.dumps(r))
+    assert type(back) is Results and np.array_equal(back.labels, r.labels)
+    assert r.__getstate__() is r.data                        # pickle state = the plain dict, as MDAnalysis does
 
 
 def test_postprocess_recovers_components(tmp_path, monkeypatch):
