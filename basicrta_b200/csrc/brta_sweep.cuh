@@ -232,6 +232,7 @@ struct SweepParams {
     RoundKeys rk;
 };
 
+
 // Shared-memory reductions of one datum: n_k += 1 and, 128 bytes further, the tick
 // accumulator, addressed in the shared window.
 __device__ __forceinline__ void red_shared_stats(uint32_t cnt_addr, uint32_t tick_bits)
@@ -240,7 +241,6 @@ __device__ __forceinline__ void red_shared_stats(uint32_t cnt_addr, uint32_t tic
                  "red.shared.add.u32 [%0+128], %1;"
                  :: "r"(cnt_addr), "r"(tick_bits) : "memory");
 }
-
 // ---- memoised cumulative rows ---------------------------------------------------------------
 // The cumulative sums of a datum depend on its tick only, and residence times are small
 // integers with huge multiplicities (half of a typical slice holds fewer than a dozen distinct
@@ -303,7 +303,7 @@ __device__ __forceinline__ uint4 lds_quad(uint32_t slice_addr, int q)
 }
 
 template <int K, bool EXACT>
-__device__ __forceinline__ void build_table_row(float tick, const float2* __restrict__ s_coef, float* __restrict__ row)
+__device__ __forceinline__ float build_table_row(float tick, const float2* __restrict__ s_coef, float* __restrict__ row)
 {
     constexpr int KP = table_row_floats(K);
     float l[KP];
@@ -333,6 +333,7 @@ __device__ __forceinline__ void build_table_row(float tick, const float2* __rest
     for (int k = K; k < KP; ++k) l[k] = cum;
 #pragma unroll
     for (int k = 0; k < KP; ++k) row[k] = l[k];
+    return cum;                                            // the row total
 }
 
 // label of one datum from its memoised row; returns true if the row underflowed (FAST only).
@@ -440,20 +441,21 @@ __device__ __forceinline__ void sweep_quad(const uint4 tk, const float4 f12, con
 // U quads of the served prefix at once: U Philox blocks and 4U row searches in flight per thread.
 // The chain of dependent shared-memory loads of one search is what the warp waits for; with
 // only four CTAs of four warps per SM the extra independent work is what fills those slots.
+// Precondition (checked once per iteration when the rows are built): no row underflowed, i.e. every
+// total is > TOTAL_FLOOR, so no datum of the prefix needs the safe path.
 #ifndef BRTA_SERVED_UNROLL
 #define BRTA_SERVED_UNROLL 2
 #endif
-template <int K, bool SAVE, bool T16, int U>
-__device__ __forceinline__ void sweep_served(uint32_t slice_addr, int q0, int qb, int kmax, int dom, uint32_t j,
+template <int K, bool SAVE, bool T16, int U, int STRIDE = THREADS>
+__device__ __forceinline__ void sweep_served(uint32_t slice_addr, int q0, int qb, int dom, uint32_t j,
                                              uint32_t chain_id, const RoundKeys& rk, uint32_t stat_addr,
-                                             uint8_t* ind_row, const int32_t* __restrict__ perm, const TableView& tab,
-                                             const float2* __restrict__ s_coef)
+                                             uint8_t* ind_row, const int32_t* __restrict__ perm, const TableView& tab)
 {
     uint32_t tis[U][4];
     float fs[U][4];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        const int q = q0 + u * THREADS;
+        const int q = q0 + u * STRIDE;
         const uint4 tk = lds_quad<T16>(slice_addr, q);
         tis[u][0] = tk.x; tis[u][1] = tk.y; tis[u][2] = tk.z; tis[u][3] = tk.w;
         const Words4 w = philox4x32_10_rk((uint32_t)(qb + q), j, chain_id, 0u, rk);
@@ -462,26 +464,13 @@ __device__ __forceinline__ void sweep_served(uint32_t slice_addr, int q0, int qb
     // label as byte offset 4 * k.  With a usable row (0 < total < inf) the last real entry equals the
     // total and u * total < total, so the count never passes K - 1 and needs no clamp.
     uint32_t off[U][4];
-    float lowest = INFINITY;
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
             float total;
             off[u][d] = search_row<K>(tis[u][d], fs[u][d], tab, total);
-            lowest = fminf(lowest, total);
         }
-    if (!(lowest > TOTAL_FLOOR)) {                         // cold: a row underflowed (FAST mode only)
-        constexpr int KP = table_row_floats(K);
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-#pragma unroll
-            for (int d = 0; d < 4; ++d) {
-                const float total = lds_f32<4 * (KP - 1)>(tab.addr + (tis[u][d] - tab.lo) * (uint32_t)(4 * table_row_stride(K)));
-                if (!(total > TOTAL_FLOOR))
-                    off[u][d] = 4u * (uint32_t)draw_label_safe<K>(tick_to_float(tis[u][d]), fs[u][d], s_coef, kmax);
-            }
-    }
     const uint32_t dom_off = 4u * (uint32_t)dom;
 #pragma unroll
     for (int u = 0; u < U; ++u)
@@ -491,10 +480,39 @@ __device__ __forceinline__ void sweep_served(uint32_t slice_addr, int q0, int qb
     if (SAVE) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int i0 = (qb + q0 + u * THREADS) * 4;        // served quads are full quads
+            const int i0 = (qb + q0 + u * STRIDE) * 4;         // served quads are full quads
 #pragma unroll
             for (int d = 0; d < 4; ++d) ind_row[perm ? perm[i0 + d] : i0 + d] = (uint8_t)(off[u][d] >> 2);
         }
+    }
+}
+
+// The served prefix of one iteration with a FIXED share per thread (BRTA_DYNAMIC = 0): quads [0, n_served) of the
+// staged slice, U at a time and the rest one at a time.  (As a separate, not inlined function -- tried to keep
+// the twenty Philox round keys out of the kernel's register allocation -- ptxas serialises the eight row
+// searches of a loop iteration: 0.93x.)
+#ifndef BRTA_SERVED_ATTR
+#define BRTA_SERVED_ATTR __forceinline__
+#endif
+template <int K, bool SAVE, bool T16>
+__device__ BRTA_SERVED_ATTR void served_prefix_sweep(uint32_t slice_addr, int n_served, int qb, int dom, uint32_t j,
+                                                 uint32_t chain_id, const RoundKeys& rk_param, uint32_t stat_addr,
+                                                 uint8_t* ind_row, const int32_t* __restrict__ perm,
+                                                 uint32_t tab_addr, uint32_t tab_lo)
+{
+    constexpr int U = BRTA_SERVED_UNROLL;
+    const RoundKeys& rk = rk_param;
+    TableView tab;
+    tab.addr = tab_addr;
+    tab.lo = tab_lo;
+    tab.limit = 0;
+    const int q_done = n_served / (U * THREADS) * (U * THREADS);
+    for (int q = threadIdx.x; q < q_done; q += U * THREADS)
+        sweep_served<K, SAVE, T16, U>(slice_addr, q, qb, dom, j, chain_id, rk, stat_addr, ind_row, perm, tab);
+    if constexpr (U > 1) {
+        const int q_one = n_served / THREADS * THREADS;
+        for (int q = q_done + threadIdx.x; q < q_one; q += THREADS)
+            sweep_served<K, SAVE, T16, 1>(slice_addr, q, qb, dom, j, chain_id, rk, stat_addr, ind_row, perm, tab);
     }
 }
 
@@ -502,29 +520,74 @@ __device__ __forceinline__ void sweep_served(uint32_t slice_addr, int q0, int qb
 // `n_served`: the first n_served quads are full quads with every tick inside the memoised rows
 // (with the chain in ascending-tick order: all the served quads); they run U at a time without
 // any per-quad case distinction, the rest through sweep_quad.
+// Work distribution inside a CTA.  Default: every thread walks a fixed share of the slice.  BRTA_DYNAMIC = 1
+// (developer builds) lets the warps claim chunks of 32 * U quads from a counter in shared memory instead, so
+// that a warp on a busier SM sub-partition claims less; measured 0.75x -- the claim (an atomic with a return
+// value plus a shuffle per chunk) costs more than the imbalance it removes.
+#ifndef BRTA_DYNAMIC
+#define BRTA_DYNAMIC 0
+#endif
+__device__ __forceinline__ int claim_chunk(uint32_t counter_addr)
+{
+    unsigned v = 0;
+    if ((threadIdx.x & 31) == 0)
+        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(v) : "r"(counter_addr) : "memory");
+    return (int)__shfl_sync(FULL, v, 0);
+}
+
 template <int K, bool EXACT, bool SAVE, bool T16>
 __device__ __forceinline__ void sweep_slice_t(uint32_t slice_addr, const float2* __restrict__ s_coef,
                                               int nq, int qb, int n_data, int kmax, int dom, uint32_t j,
-                                              uint32_t chain_id, const RoundKeys& rk,
+                                              uint32_t chain_id, const RoundKeys& rk, uint32_t next_addr,
                                               const float4* __restrict__ u_row, uint32_t stat_addr,
                                               uint8_t* ind_row, const int32_t* __restrict__ perm, const TableView& tab,
                                               int n_served)
 {
-    constexpr int U = BRTA_SERVED_UNROLL;
-    int q_done = 0;
-    if (u_row == nullptr) {                                // injected uniforms (tests) take the general loop
-        q_done = n_served / (U * THREADS) * (U * THREADS);
-        for (int q = threadIdx.x; q < q_done; q += U * THREADS)
-            sweep_served<K, SAVE, T16, U>(slice_addr, q, qb, kmax, dom, j, chain_id, rk, stat_addr, ind_row, perm, tab, s_coef);
-        if constexpr (U > 1) {
-            const int q_one = n_served / THREADS * THREADS;
-            for (int q = q_done + threadIdx.x; q < q_one; q += THREADS)
-                sweep_served<K, SAVE, T16, 1>(slice_addr, q, qb, kmax, dom, j, chain_id, rk, stat_addr, ind_row, perm, tab, s_coef);
-            q_done = q_one;
-        }
-    }
     // at most one quad of the whole chain is partial; find out once whether it is in this slice
     const int tail_q = ((n_data & 3) != 0) ? (n_data >> 2) - qb : -1;
+#if BRTA_DYNAMIC
+    constexpr int U = BRTA_SERVED_UNROLL;
+    const int lane = threadIdx.x & 31;
+    // served prefix: chunks of 32 * U quads, lane handles quads lane, lane + 32, ... of its chunk
+    const int n_chunks = (u_row == nullptr) ? n_served / (32 * U) : 0;   // injected uniforms (tests): general loop only
+    if (n_chunks > 0) {
+        int c = claim_chunk(next_addr);
+        while (c < n_chunks) {
+            const int c_next = claim_chunk(next_addr);
+            sweep_served<K, SAVE, T16, U, 32>(slice_addr, c * (32 * U) + lane, qb, dom, j, chain_id, rk, stat_addr,
+                                              ind_row, perm, tab);
+            c = c_next;
+        }
+    }
+    // the rest (end of the prefix, recomputed tail, partial quad): chunks of 32 quads through the general path
+    const int rest0 = n_chunks * (32 * U);
+    const int n_rest = (nq - rest0 + 31) / 32;
+    int c = n_rest > 0 ? claim_chunk(next_addr + 4u) : 0;
+    while (c < n_rest) {
+        const int c_next = claim_chunk(next_addr + 4u);
+        const int q = rest0 + c * 32 + lane;
+        if (q < nq) {
+            const uint4 tk = lds_quad<T16>(slice_addr, q);
+            float4 f12;
+            if (u_row != nullptr) {
+                const float4 uu = u_row[qb + q];
+                f12 = make_float4(uu.x + 1.0f, uu.y + 1.0f, uu.z + 1.0f, uu.w + 1.0f);
+            } else {
+                const Words4 w = philox4x32_10_rk((uint32_t)(qb + q), j, chain_id, 0u, rk);
+                f12 = make_float4(word_to_12(w.x), word_to_12(w.y), word_to_12(w.z), word_to_12(w.w));
+            }
+            sweep_quad<K, EXACT, SAVE>(tk, f12, s_coef, kmax, dom, (qb + q) * 4, n_data, q == tail_q,
+                                       stat_addr, ind_row, perm, tab);
+        }
+        c = c_next;
+    }
+#else
+    int q_done = 0;
+    if (u_row == nullptr && n_served >= THREADS) {         // injected uniforms (tests) take the general loop
+        served_prefix_sweep<K, SAVE, T16>(slice_addr, n_served, qb, dom, j, chain_id, rk, stat_addr, ind_row, perm,
+                                          tab.addr, tab.lo);
+        q_done = n_served / THREADS * THREADS;
+    }
     for (int q = q_done + threadIdx.x; q < nq; q += THREADS) {
         const uint4 tk = lds_quad<T16>(slice_addr, q);
         float4 f12;
@@ -538,21 +601,22 @@ __device__ __forceinline__ void sweep_slice_t(uint32_t slice_addr, const float2*
         sweep_quad<K, EXACT, SAVE>(tk, f12, s_coef, kmax, dom, (qb + q) * 4, n_data, q == tail_q,
                                    stat_addr, ind_row, perm, tab);
     }
+#endif
 }
 
 template <int K, bool EXACT, bool SAVE>
 __device__ __forceinline__ void sweep_slice(uint32_t slice_addr, bool ticks16, const float2* __restrict__ s_coef,
                                             int nq, int qb, int n_data, int kmax, int dom, uint32_t j,
-                                            uint32_t chain_id, const RoundKeys& rk,
+                                            uint32_t chain_id, const RoundKeys& rk, uint32_t next_addr,
                                             const float4* __restrict__ u_row, uint32_t stat_addr,
                                             uint8_t* ind_row, const int32_t* __restrict__ perm, const TableView& tab,
                                             int n_served)
 {
     if (ticks16)
-        sweep_slice_t<K, EXACT, SAVE, true>(slice_addr, s_coef, nq, qb, n_data, kmax, dom, j, chain_id, rk, u_row,
+        sweep_slice_t<K, EXACT, SAVE, true>(slice_addr, s_coef, nq, qb, n_data, kmax, dom, j, chain_id, rk, next_addr, u_row,
                                             stat_addr, ind_row, perm, tab, n_served);
     else
-        sweep_slice_t<K, EXACT, SAVE, false>(slice_addr, s_coef, nq, qb, n_data, kmax, dom, j, chain_id, rk, u_row,
+        sweep_slice_t<K, EXACT, SAVE, false>(slice_addr, s_coef, nq, qb, n_data, kmax, dom, j, chain_id, rk, next_addr, u_row,
                                              stat_addr, ind_row, perm, tab, n_served);
 }
 
@@ -584,16 +648,27 @@ __device__ __forceinline__ int served_prefix(const unsigned char* __restrict__ s
     return (int)r;
 }
 
-// Developer-only phase timing (-DBRTA_PHASE_TIMING builds a debug library): thread 0 of
-// every CTA accumulates clock64 deltas per phase into g_phase[blockIdx.x][8].
+// Developer-only phase timing (-DBRTA_PHASE_TIMING builds a debug library): thread 0 of every CTA
+// accumulates clock64 deltas of phases 0-4, lane 0 of the lead warp those of phases 5-7, into
+// g_phase[blockIdx.x][8].
 #ifdef BRTA_PHASE_TIMING
 __device__ unsigned long long* g_phase = nullptr;
 #define PHASE_DECL long long ph_t = clock64(); unsigned long long ph_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define PHASE_MARK(i) do { if (threadIdx.x == 0) { const long long now = clock64(); ph_acc[i] += (unsigned long long)(now - ph_t); ph_t = now; } } while (0)
-#define PHASE_FLUSH do { if (threadIdx.x == 0 && g_phase) for (int i = 0; i < 8; ++i) g_phase[blockIdx.x * 8 + i] += ph_acc[i]; } while (0)
+#define PHASE_LEAD_ARG , ph_acc
+#define PHASE_LEAD_PARAM , unsigned long long* ph_acc
+#define PHASE_LEAD_BEGIN long long ph_t = clock64();
+#define PHASE_LEAD_MARK(i) do { if ((threadIdx.x & 31) == 0) { const long long now = clock64(); ph_acc[i] += (unsigned long long)(now - ph_t); ph_t = now; } } while (0)
+#define PHASE_FLUSH do { if (g_phase) { \
+        if (threadIdx.x == 0) for (int i = 0; i < 5; ++i) atomicAdd(&g_phase[blockIdx.x * 8 + i], ph_acc[i]); \
+        if (warp == lead && lane == 0) for (int i = 5; i < 8; ++i) atomicAdd(&g_phase[blockIdx.x * 8 + i], ph_acc[i]); } } while (0)
 #else
 #define PHASE_DECL
 #define PHASE_MARK(i)
+#define PHASE_LEAD_ARG
+#define PHASE_LEAD_PARAM
+#define PHASE_LEAD_BEGIN
+#define PHASE_LEAD_MARK(i)
 #define PHASE_FLUSH
 #endif
 
@@ -618,10 +693,12 @@ __device__ __forceinline__ void named_barrier_sync(int id, int nthreads)
 constexpr int min_ctas(int k) { return k <= 16 ? BRTA_MIN_CTAS_SMALLK : BRTA_MIN_CTAS_LARGEK; }
 
 // ---- waiting on other CTAs / GPUs -------------------------------------------------------------
-// Polls are tight (no back-off: the word that ends a wait is at most one L2 / NVLink round trip
-// away); the watchdog reads the nanosecond timer once per 4096 polls and gives up after
-// `limit_ns` (brta_batch.watchdog_ns; the host scales it from the schedule's makespan), so a
-// teammate that never posts cannot hang the device.
+// A waiting warp sleeps a few tens of nanoseconds between polls: a tight poll loop keeps the SM's
+// memory pipe busy and slows the co-resident CTAs that are sweeping (measured: -20 % on the whole
+// run).  Long waits (a team mate still finishing its previous wave) back off to 0.5 us.  The
+// watchdog reads the nanosecond timer once per 4096 polls and gives up after `limit_ns`
+// (brta_batch.watchdog_ns; the host scales it from the schedule's makespan), so a teammate that
+// never posts cannot hang the device.
 __device__ __forceinline__ unsigned long long global_timer_ns()
 {
     unsigned long long t;
@@ -631,8 +708,10 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
 struct Watchdog {
     unsigned spins = 0;
     unsigned long long t0 = 0;
-    __device__ __forceinline__ bool expired(unsigned long long limit_ns)
+    // one unsuccessful poll: sleep `short_ns` (the first 64 times) or 500 ns, then check the clock now and then
+    __device__ __forceinline__ bool expired(unsigned long long limit_ns, unsigned short_ns = 20u)
     {
+        __nanosleep(spins < 64u ? short_ns : 500u);
         if ((++spins & 4095u) != 0u) return false;
         const unsigned long long now = global_timer_ns();
         if (t0 == 0ull) { t0 = now; return false; }
@@ -651,17 +730,266 @@ __device__ __forceinline__ void st_relaxed_sys_v2(unsigned long long* p, unsigne
     asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" :: "l"(p), "l"(a), "l"(b) : "memory");
 }
 
-// Phases of one iteration of one CTA (PHASE_MARK indices of the developer build):
-//   0 table build   1 wait C   2 sweep   3 wait A   4 partials + post   5 gather (waits for the team)
-//   6 posterior     7 store
+// ---- the serial part of an iteration: ONE warp (lane = component) -----------------------------------
+// This CTA's partial statistics -> team (and cross-GPU) exchange -> totals -> Dirichlet / Gamma update
+// (gibbs.py:210-211) -> coefficients of the next iteration into shared memory.  Every member of a team
+// (and every GPU of a sharded chain) computes the same update from the same Philox key, so nothing is
+// broadcast.  Not inlined: its registers are not the sweep's.
+#ifdef BRTA_SERIAL_NOINLINE                               // measured: a call here costs 5-7 % of the whole run
+#define BRTA_SERIAL_ATTR __noinline__
+#else
+#define BRTA_SERIAL_ATTR __forceinline__
+#endif
+template <int K>
+__device__ BRTA_SERIAL_ATTR void serial_part(const SweepParams& prm, const brta_task task, const int j, const int par,
+                                             int dom, const unsigned slice_n, const unsigned long long slice_t,
+                                             const bool save, const int row, const int rows,
+                                             const uint32_t key0, const uint32_t key1,
+                                             unsigned (*s_stat)[64], float2* s_coef, float (*s_hyp)[32], const float* s_rhb,
+                                             int* s_dom, unsigned* s_bad, unsigned* s_abort PHASE_LEAD_PARAM)
+{
+    constexpr bool HALF = K <= 16;
+    constexpr int PASSES = HALF ? 1 : 2;
+    const brta_batch& b = prm.b;
+    PHASE_LEAD_BEGIN
+    const int lane = threadIdx.x & 31;
+    const int r = task.chain;
+    const int team = task.team_size;
+    const int kreal = b.ncomp;
+    const int niter = b.niter;
+    const int j_begin = b.iter_begin;
+    const int j_end = b.iter_end > 0 ? b.iter_end : niter;
+    const int n_shards = b.n_shards > 1 ? b.n_shards : 1;
+    const bool sharded = n_shards > 1;                     // the chain continues on other GPUs
+    const bool mailbox = !sharded && team > 1 && team <= BRTA_MAILBOX_MAX_TEAM;
+    const bool inject_coef = (b.flags & BRTA_FLAG_INJECT_COEF) != 0;
+    const bool trace = (b.flags & BRTA_FLAG_TRACE) != 0;
+    const unsigned long long wd_limit = b.watchdog_ns ? b.watchdog_ns : 60000000000ull;
+    const uint32_t chain_id = b.chain_id[r];
+    const int comp = HALF ? (lane & 15) : lane;            // component this lane draws for
+    const bool own = lane < kreal;                         // lane holds the statistics / coefficients of component `lane`
+    const bool live = comp < kreal;
+    unsigned char* const exch = static_cast<unsigned char*>(b.exchange) + b.exch_offset[r];
+    // mailbox layout: slot[parity][member][32] of {tag<<32 | n_k, tag<<32 | tick sum}
+    ulonglong2* const mbox = reinterpret_cast<ulonglong2*>(exch);
+    // atomics layout (teams larger than the mailbox limit)
+    unsigned long long* const ex_sum = reinterpret_cast<unsigned long long*>(exch + EXCH_SUM_OFF);
+    unsigned* const ex_cnt = reinterpret_cast<unsigned*>(exch + EXCH_CNT_OFF);
+    unsigned* const ex_arrive = reinterpret_cast<unsigned*>(exch + EXCH_ARRIVE_OFF);
+    bool abort = false;
+
+    // ---- this CTA's partials; the uncounted dominant label follows by subtraction --
+    unsigned cnt = s_stat[par][lane];
+    unsigned long long sum = s_stat[par][32 + lane];
+    s_stat[par][lane] = 0;                                 // ready for iteration j + 2
+    s_stat[par][32 + lane] = 0;
+    {
+        const unsigned oc = __reduce_add_sync(FULL, cnt);
+        const unsigned os = __reduce_add_sync(FULL, (unsigned)sum);
+        if (lane == dom) { cnt = slice_n - oc; sum = (unsigned)(slice_t - os); }
+    }
+    Watchdog wd;
+    if (mailbox) {
+        if (own) {
+            const unsigned long long tag = (unsigned long long)(unsigned)j << 32;
+            st_relaxed_v2(&mbox[((size_t)par * team + task.team_rank) * 32 + lane], tag | cnt, tag | sum);
+        }
+    } else if (team > 1 || sharded) {
+        // large team: L2 atomics + monotonic arrive counter (3 rotating buffers).  On a sharded chain
+        // the CTA that arrives LAST holds the GPU's totals and sends them to every GPU's mailbox over
+        // NVLink as tagged 64-bit words {iteration | n_k}, {iteration | sum lo}, {iteration | sum hi}.
+        const int buf = j % 3;
+        if (cnt != 0u) {
+            atomicAdd(&ex_cnt[buf * 32 + lane], cnt);
+            atomicAdd(&ex_sum[buf * 32 + lane], sum);
+        }
+        __syncwarp();
+        unsigned prev = 0;
+        if (lane == 0) {
+            __threadfence();
+            prev = atomicAdd(ex_arrive, 1u);
+        }
+        if (sharded) {
+            prev = __shfl_sync(FULL, prev, 0);
+            if (prev + 1u == (unsigned)team * (unsigned)(j - j_begin)) {   // the counter starts at 0 every launch
+                __threadfence();
+                const unsigned g_c = ld_relaxed_u32(&ex_cnt[buf * 32 + lane]);
+                const unsigned long long g_s = ld_relaxed_u64(&ex_sum[buf * 32 + lane]);
+                const unsigned long long tag = (unsigned long long)(unsigned)j << 32;
+                const size_t slot = (((size_t)par * n_shards + b.shard_rank) * 32 + lane) * 4;
+                if (own) {
+                    for (int g = 0; g < n_shards; ++g) {
+                        unsigned long long* const dst = static_cast<unsigned long long*>(b.shard_mailbox[g]) + slot;
+                        st_relaxed_sys_v2(dst, tag | g_c, tag | (g_s & 0xffffffffull));
+                        st_relaxed_sys_u64(dst + 2, tag | (g_s >> 32));
+                    }
+                }
+            }
+        }
+        if (task.team_rank == 0) {                         // recycle the buffer last read in j-1
+            const int old = (j + 2) % 3;
+            ex_cnt[old * 32 + lane] = 0u;
+            ex_sum[old * 32 + lane] = 0ull;
+        }
+    }
+    // shape-independent half of the Marsaglia-Tsang trials, overlapped with the exchange
+    TrialRandoms rnd[PASSES][NTRIALS];
+    if (!inject_coef) {
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p) {
+            const uint32_t purpose = ((HALF ? (lane >> 4) : p) == 0 ? 1u : 2u) + 4u * (uint32_t)comp;
+#pragma unroll
+            for (int t = 0; t < NTRIALS; ++t)
+                rnd[p][t] = trial_randoms(philox4x32_10_rk((uint32_t)t, (uint32_t)j, chain_id, purpose, prm.rk));
+        }
+    }
+    PHASE_LEAD_MARK(5);
+    // ---- team totals -------------------------------------------------------------------------
+    unsigned tot_c = cnt;
+    unsigned long long tot_s = sum;
+    if (mailbox) {
+        // lane = component; K <= 16: the upper half-warp takes the odd members.  All loads of a
+        // round are in flight together; a word is valid once it carries this iteration's tag.
+        constexpr int SPLIT = HALF ? 2 : 1;
+        constexpr int ROUND = 16;
+        tot_c = 0;
+        tot_s = 0;
+        if (live) {
+            const ulonglong2* const base = &mbox[(size_t)par * team * 32 + comp];
+            for (int m0 = HALF ? (lane >> 4) : 0; m0 < team && !abort; m0 += ROUND * SPLIT) {
+                unsigned pend = 0;
+#pragma unroll
+                for (int i = 0; i < ROUND; ++i)
+                    if (m0 + i * SPLIT < team) pend |= 1u << i;
+                while (pend) {
+                    ulonglong2 v[ROUND];
+#pragma unroll
+                    for (int i = 0; i < ROUND; ++i)
+                        if (pend & (1u << i)) v[i] = ld_relaxed_v2(&base[(size_t)(m0 + i * SPLIT) * 32]);
+#pragma unroll
+                    for (int i = 0; i < ROUND; ++i) {
+                        if ((pend & (1u << i)) && (unsigned)(v[i].x >> 32) == (unsigned)j &&
+                            (unsigned)(v[i].y >> 32) == (unsigned)j) {
+                            tot_c += (unsigned)v[i].x;
+                            tot_s += (unsigned)v[i].y;
+                            pend &= ~(1u << i);
+                        }
+                    }
+                    if (pend && wd.expired(wd_limit)) { abort = true; break; }
+                }
+            }
+        }
+        if constexpr (HALF) {
+            tot_c += __shfl_xor_sync(FULL, tot_c, 16);
+            tot_s += __shfl_xor_sync(FULL, tot_s, 16);
+        }
+    } else if (sharded) {
+        // every CTA of every GPU reads the G shards' totals from its GPU's own mailbox
+        const unsigned long long* const mine = static_cast<const unsigned long long*>(b.shard_mailbox[b.shard_rank]);
+        tot_c = 0;
+        tot_s = 0;
+        if (own) {
+            for (int g = 0; g < n_shards && !abort; ++g) {
+                const unsigned long long* const src = mine + (((size_t)par * n_shards + g) * 32 + lane) * 4;
+                for (;;) {
+                    const ulonglong2 w01 = ld_relaxed_sys_v2(src);
+                    const unsigned long long w2 = ld_relaxed_sys_u64(src + 2);
+                    if ((unsigned)(w01.x >> 32) == (unsigned)j && (unsigned)(w01.y >> 32) == (unsigned)j &&
+                        (unsigned)(w2 >> 32) == (unsigned)j) {
+                        tot_c += (unsigned)w01.x;
+                        tot_s += (w01.y & 0xffffffffull) | (w2 << 32);
+                        break;
+                    }
+                    if (wd.expired(wd_limit)) { abort = true; break; }
+                }
+            }
+        }
+    } else if (team > 1) {
+        const int buf = j % 3;
+        const unsigned target = (unsigned)team * (unsigned)(j - j_begin);
+        while (ld_acquire_u32(ex_arrive) < target)
+            if (wd.expired(wd_limit)) { abort = true; break; }
+        tot_c = ld_relaxed_u32(&ex_cnt[buf * 32 + lane]);
+        tot_s = ld_relaxed_u64(&ex_sum[buf * 32 + lane]);
+    }
+    if (__any_sync(FULL, abort)) {                         // rendezvous watchdog: give the chain up
+        if (lane == 0) *s_abort = 1u;
+        return;
+    }
+    PHASE_LEAD_MARK(6);
+
+    if (trace && task.team_rank == 0 && own) {
+        const size_t o = ((size_t)r * niter + (j - 1)) * kreal + lane;
+        b.trace_nk[o] = (int64_t)tot_c;
+        b.trace_tk[o] = (int64_t)tot_s;
+    }
+    // next iteration skips the most populated label in the atomics
+    {
+        const unsigned keyv = own ? ((tot_c << 5) | (unsigned)(31 - lane)) : 0u;
+        dom = 31 - (int)(__reduce_max_sync(FULL, keyv) & 31u);
+        if (lane == 0) *s_dom = dom;
+    }
+
+    // ---- posterior update (gibbs.py:210-211): lane = component ---------------------------------
+    float2 ca = make_float2(-INFINITY, 0.0f);
+    bool bad = false;
+    if (inject_coef) {
+        if (own && j < j_end) {
+            const size_t o = ((size_t)r * niter + j) * kreal + lane;
+            ca = make_float2(b.inj_c[o], b.inj_a[o]);
+            bad = !coef_ok(ca);
+        }
+    } else {
+        const float ts = b.ts[r];
+        const float fcnt = (float)tot_c;
+        float l2g[PASSES];
+#pragma unroll
+        for (int p = 0; p < PASSES; ++p) {
+            const float n_c = HALF ? __shfl_sync(FULL, fcnt, comp) : fcnt;
+            const uint32_t purpose = ((HALF ? (lane >> 4) : p) == 0 ? 1u : 2u) + 4u * (uint32_t)comp;
+            l2g[p] = log2_gamma<NTRIALS>(s_hyp[p][lane] + n_c, rnd[p], (uint32_t)j, chain_id, purpose, key0, key1, live);
+        }
+        // log2 of the weight gamma y_k and of the rate r_k = G_k / (b + T_k), for component `lane`
+        const float l2den = __log2f(fmaf((float)tot_s, ts, s_rhb[lane]));
+        const float l2y = l2g[0];
+        const float l2r = (HALF ? __shfl_down_sync(FULL, l2g[0], 16) : l2g[PASSES - 1]) - l2den;
+        const float rate = fast_exp2(l2r);
+        // The indicator draw is invariant to a common factor of the weights (the inverse CDF is
+        // taken at u * total), so the sweep runs on the UNNORMALISED Dirichlet gammas:
+        // c_k = log2(y_k r_k); the weights are normalised only for the stored rows.
+        if (own) ca = make_float2(l2y + l2r, rate * (ts * LOG2E));
+        // a usable row: every slope finite and >= 0, every intercept finite or -inf (a dead
+        // component), at least one alive
+        bad = (own && !coef_ok(ca)) || !__any_sync(FULL, own && ca.x > -INFINITY);
+        if (save && task.team_rank == 0 && row < rows) {
+            const float y = own ? l2y : -INFINITY;
+            const float mx = warp_max(y);
+            const float tot = warp_sum(own ? fast_exp2(y - mx) : 0.0f);
+            if (own) {
+                const size_t o = ((size_t)r * rows + row) * kreal + lane;
+                b.mcweights[o] = exp2((double)(y - mx - __log2f(tot)));
+                b.mcrates[o] = (double)rate;
+            }
+        }
+    }
+    s_coef[lane] = ca;
+    if (__any_sync(FULL, bad) && lane == 0) *s_bad = 1u;
+    PHASE_LEAD_MARK(7);
+}
+
+// Phases of one iteration of one CTA (PHASE_MARK indices of the developer build; 0-4 are timed by thread 0,
+// 5-7 by lane 0 of the lead warp):
+//   0 table build   1 wait C   2 sweep   3 wait A   4 serial part + wait B (as seen by thread 0)
+//   5 partials + post + trial randoms   6 gather (waits for the team)   7 posterior + store
 //
-// Per iteration a CTA passes TWO block-wide barriers: C (memoised rows complete) and A (statistics
-// complete).  Everything between A and C -- partials, team exchange, posterior draw, new coefficients,
-// this warp's share of the rows -- is done by EVERY warp on its own (lane = component, same inputs,
-// same Philox key, hence the same bits), so the serial part of an iteration has no hand-off between
-// warps: the first kernel generation passed five barriers and ran the draw in one warp while three
-// waited.  The statistics are double-buffered by iteration parity so that the warps may read them at
-// their own pace.
+// Per iteration a CTA passes THREE block-wide barriers: C (memoised rows complete), A (statistics complete)
+// and B (new coefficients published).  Between A and B only the LEAD warp works -- partials, team exchange,
+// posterior draw (lane = component; Dirichlet and rate gammas in the two half-warps for K <= 16), stored row,
+// new coefficients -- while the other warps wait at B without taking issue slots from the co-resident CTAs
+// that are sweeping.  (Generation 2 let every warp run that part redundantly to save the barrier: the
+// serial part got shorter, but its four copies slowed every co-resident sweep down by 45 %; 0.80x overall.)
+// All of the lead warp's state lives in shared memory between iterations, so the sweep's register
+// allocation carries none of it.
 template <int K, bool EXACT>
 __global__ void __launch_bounds__(THREADS, min_ctas(K))
 gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
@@ -672,7 +1000,9 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
     const brta_batch& b = prm.b;
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
-    __shared__ __align__(16) float2 s_coef_w[WARPS][32];   // {coef_c, coef_a}: one private copy per warp
+    __shared__ __align__(16) float2 s_coef[32];            // {coef_c, coef_a} of the running iteration
+    __shared__ float s_hyp[2][32];                         // prior shapes of the gammas a lane draws (per pass)
+    __shared__ float s_rhb[32];                            // prior rate of the rate gamma (gibbs.py:174)
     // this CTA's statistics, [parity][0..31] n_k, [parity][32..63] tick sums (fit 32 bits: host-checked)
     __shared__ __align__(16) unsigned s_stat[2][64];
     __shared__ __align__(16) float s_table[TABLE_FLOATS + 32];  // memoised cumulative rows of the running iteration (+ probe overrun)
@@ -684,12 +1014,15 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
     __shared__ unsigned s_red_n[WARPS];
     __shared__ unsigned s_bad;
     __shared__ unsigned s_abort;                           // rendezvous watchdog tripped
+    __shared__ int s_dom;                                  // label left out of the atomics in the next sweep
+    __shared__ unsigned s_next[2];                         // chunk counters of the running sweep (served prefix, rest)
+    const uint32_t next_addr = opaque_u32((uint32_t)__cvta_generic_to_shared(&s_next[0]));
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    // The warp that posts the CTA's partials, stores rows and resets buffers.  Warp w of every CTA sits on
-    // SM sub-partition w % 4; rotating the role over the co-resident CTAs spreads it over the four schedulers.
+    // The warp that runs the serial part.  Warp w of every CTA sits on SM sub-partition w % 4; rotating the
+    // role over the co-resident CTAs spreads it over the four schedulers.
     const int lead = (int)((blockIdx.x + blockIdx.x / max(gridDim.x >> 2, 1u)) & (WARPS - 1));
     const uint32_t key0 = (uint32_t)b.seed;
     const uint32_t key1 = (uint32_t)(b.seed >> 32);
@@ -701,12 +1034,6 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
     const int j_end = b.iter_end > 0 ? b.iter_end : niter;
     const bool inject_coef = (b.flags & BRTA_FLAG_INJECT_COEF) != 0;
     const bool inject_u = (b.flags & BRTA_FLAG_INJECT_U) != 0;
-    const bool trace = (b.flags & BRTA_FLAG_TRACE) != 0;
-    const unsigned long long wd_limit = b.watchdog_ns ? b.watchdog_ns : 60000000000ull;
-
-    const int comp = HALF ? (lane & 15) : lane;            // component this lane draws for
-    const bool own = lane < kreal;                         // lane holds the statistics / coefficients of component `lane`
-    const bool live = comp < kreal;
 
     const int task_end = b.cta_task_begin[blockIdx.x + 1];
     for (int ti = b.cta_task_begin[blockIdx.x]; ti < task_end; ++ti) {
@@ -715,14 +1042,9 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
         const int n_data = b.n_data[r];
         const int nq = task.quad_count;
         const int qb = task.quad_begin;
-        const int team = task.team_size;
-        const int n_shards = b.n_shards > 1 ? b.n_shards : 1;
-        const bool sharded = n_shards > 1;                 // the chain continues on other GPUs
-        const bool mailbox = !sharded && team > 1 && team <= BRTA_MAILBOX_MAX_TEAM;
         const uint32_t chain_id = b.chain_id[r];
         // a chain whose largest tick fits 16 bits keeps its slice in shared memory at 8 B per quad
         const bool ticks16 = b.max_tick[r] < 65536u;
-        const float ts = b.ts[r];
         const int64_t tick_off = b.tick_offset[r];
         const int ind_stride = b.ind_stride[r];
         uint8_t* const ind_base = b.indicator + b.ind_offset[r];
@@ -764,10 +1086,34 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
         my_hi = __reduce_max_sync(FULL, my_hi);
         if (lane == 0) { s_red_n[warp] = my_n; s_red_t[warp] = my_t; s_red_lo[warp] = my_lo; s_red_hi[warp] = my_hi; }
         if (tid < 64) { s_stat[0][tid] = 0; s_stat[1][tid] = 0; }
-        if (tid == 0) { s_bad = 0; s_abort = 0; }
+        if (tid == 0) { s_bad = 0; s_abort = 0; s_dom = 0; s_next[0] = 0; s_next[1] = 0; }
+        if (warp == 0) {
+            // coefficients of the first iteration of this launch and the priors: lane = component
+            float2 ca = make_float2(-INFINITY, 0.0f);
+            if (lane < kreal) {
+                if (inject_coef) {
+                    const size_t o = ((size_t)r * niter + j_begin) * kreal + lane;
+                    ca = make_float2(b.inj_c[o], b.inj_a[o]);
+                    if (!coef_ok(ca)) atomicOr(&s_bad, 1u);
+                } else {
+                    ca = make_float2(b.init_c[(size_t)r * kreal + lane], b.init_a[(size_t)r * kreal + lane]);
+                }
+            }
+            s_coef[lane] = ca;
+            // s_hyp[p][lane]: prior shape of the gamma this lane draws in pass p (HALF: Dirichlet below lane 16, rate above)
+            const int comp = HALF ? (lane & 15) : lane;
+#pragma unroll
+            for (int p = 0; p < PASSES; ++p) {
+                const int type = HALF ? (lane >> 4) : p;
+                float h = 1.0f;
+                if (comp < kreal) h = type == 0 ? b.whyper[(size_t)r * kreal + comp] : b.rhyper[((size_t)r * kreal + comp) * 2 + 0];
+                s_hyp[p][lane] = h;
+            }
+            s_rhb[lane] = lane < kreal ? b.rhyper[((size_t)r * kreal + lane) * 2 + 1] : 1.0f;
+        }
         __syncthreads();
 
-        // slice totals and tick range (every warp), priors of this lane's component
+        // slice totals and tick range (every warp)
         unsigned slice_n = 0;
         unsigned long long slice_t = 0;
         unsigned tick_lo = 0xffffffffu, tick_hi = 0u;
@@ -778,16 +1124,6 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
             tick_lo = min(tick_lo, s_red_lo[w]);
             tick_hi = max(tick_hi, s_red_hi[w]);
         }
-        // hyp[p]: prior shape of the gamma this lane draws in pass p (HALF: Dirichlet for lanes < 16, rate above)
-        float hyp[PASSES];
-        float rh_b = 1.0f;
-#pragma unroll
-        for (int p = 0; p < PASSES; ++p) {
-            const int type = HALF ? (lane >> 4) : p;
-            hyp[p] = 1.0f;
-            if (live) hyp[p] = type == 0 ? b.whyper[(size_t)r * kreal + comp] : b.rhyper[((size_t)r * kreal + comp) * 2 + 0];
-        }
-        if (own) rh_b = b.rhyper[((size_t)r * kreal + lane) * 2 + 1];
         // memoised rows cover ticks lo .. lo + table_rows - 1 of this slice
         int table_rows = 0;
         if (!(b.flags & BRTA_FLAG_NO_TABLE) && tick_lo <= tick_hi)
@@ -797,44 +1133,25 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
         tab.lo = tick_lo;
         tab.limit = table_rows > 0 ? tick_lo + (unsigned)table_rows : 0u;
         const int n_served = served_prefix(smem_raw, ticks16, nq, qb, n_data, tab.limit, s_red_lo);
-        unsigned char* const exch = static_cast<unsigned char*>(b.exchange) + b.exch_offset[r];
-        // mailbox layout: slot[parity][member][32] of {tag<<32 | n_k, tag<<32 | tick sum}
-        ulonglong2* const mbox = reinterpret_cast<ulonglong2*>(exch);
-        // atomics layout (teams larger than the mailbox limit)
-        unsigned long long* const ex_sum = reinterpret_cast<unsigned long long*>(exch + EXCH_SUM_OFF);
-        unsigned* const ex_cnt = reinterpret_cast<unsigned*>(exch + EXCH_CNT_OFF);
-        unsigned* const ex_arrive = reinterpret_cast<unsigned*>(exch + EXCH_ARRIVE_OFF);
 
-        // coefficients of the first iteration of this launch: lane = component
-        float2 ca = make_float2(-INFINITY, 0.0f);
-        bool bad = false;
-        if (own) {
-            if (inject_coef) {
-                const size_t o = ((size_t)r * niter + j_begin) * kreal + lane;
-                ca = make_float2(b.inj_c[o], b.inj_a[o]);
-                bad |= !coef_ok(ca);
-            } else {
-                ca = make_float2(b.init_c[(size_t)r * kreal + lane], b.init_a[(size_t)r * kreal + lane]);
-            }
-        }
-        int dom = 0;
         unsigned long long busy_cycles = 0;                // schedule feedback: iteration start -> statistics complete
         PHASE_DECL
         for (int j = j_begin + 1; j <= j_end; ++j) {
             const long long iter_t0 = b.task_cycles ? clock64() : 0;
-            // ---- this warp's copy of the coefficients and its share of the memoised rows -------
-            s_coef_w[warp][lane] = ca;
-            __syncwarp();
-            const float2* const s_coef = s_coef_w[warp];
-            for (int rr = tid; rr < table_rows; rr += THREADS)
-                build_table_row<K, EXACT>((float)(tick_lo + (unsigned)rr), s_coef,
-                                          s_table + (size_t)rr * table_row_stride(K));
+            // ---- this thread's share of the memoised rows ---------------------------------------
+            bool row_bad = false;                          // FAST mode: a row whose every term underflowed
+            for (int rr = tid; rr < table_rows; rr += THREADS) {
+                const float total = build_table_row<K, EXACT>((float)(tick_lo + (unsigned)rr), s_coef,
+                                                              s_table + (size_t)rr * table_row_stride(K));
+                row_bad |= !(total > TOTAL_FLOOR);
+            }
             PHASE_MARK(0);
-            __syncthreads();                               // C: rows complete; everyone is done with iteration j-1
+            // C: rows complete.  If any row underflowed (early burn-in states at most) no quad takes the
+            // unchecked served loop in this iteration; the general loop redoes such data with max subtraction.
+            const int n_served_j = __syncthreads_or(!EXACT && row_bad) ? 0 : n_served;
             PHASE_MARK(1);
-            if (s_abort) break;                            // uniform: written before the barrier
             const int par = j & 1;
-            if (warp == lead) { s_stat[par ^ 1][lane] = 0; s_stat[par ^ 1][32 + lane] = 0; }   // for iteration j+1
+            const int dom = s_dom;
             const uint32_t stat_addr = stat_addr0 + 256u * (uint32_t)par;
             const bool save = (j % thin == 0);
             const int row = j / thin - 1;
@@ -844,215 +1161,29 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
             // ---- indicator draws + sufficient statistics (gibbs.py:196-207) -------------
             if (save)
                 sweep_slice<K, EXACT, true>(slice_addr, ticks16, s_coef, nq, qb, n_data, kreal - 1, dom, (uint32_t)j, chain_id,
-                                            prm.rk, u_row, stat_addr, ind_base + (size_t)row * ind_stride, perm, tab, n_served);
+                                            prm.rk, next_addr, u_row, stat_addr, ind_base + (size_t)row * ind_stride, perm, tab, n_served_j);
             else
                 sweep_slice<K, EXACT, false>(slice_addr, ticks16, s_coef, nq, qb, n_data, kreal - 1, dom, (uint32_t)j, chain_id,
-                                             prm.rk, u_row, stat_addr, nullptr, nullptr, tab, n_served);
+                                             prm.rk, next_addr, u_row, stat_addr, nullptr, nullptr, tab, n_served_j);
             PHASE_MARK(2);
             __syncthreads();                               // A: this CTA's statistics are complete
             PHASE_MARK(3);
+            if (tid == 0) { s_next[0] = 0; s_next[1] = 0; }  // for the next sweep (two barriers away)
             if (b.task_cycles && 2 * (j - j_begin) > j_end - j_begin) busy_cycles += (unsigned long long)(clock64() - iter_t0);
 
-            // ---- this CTA's partials; the uncounted dominant label follows by subtraction --
-            unsigned cnt = s_stat[par][lane];
-            unsigned long long sum = s_stat[par][32 + lane];
-            {
-                const unsigned oc = __reduce_add_sync(FULL, cnt);
-                const unsigned os = __reduce_add_sync(FULL, (unsigned)sum);
-                if (lane == dom) { cnt = slice_n - oc; sum = (unsigned)(slice_t - os); }
-            }
-            Watchdog wd;
-            if (mailbox) {
-                if (warp == lead && own) {
-                    const unsigned long long tag = (unsigned long long)(unsigned)j << 32;
-                    st_relaxed_v2(&mbox[((size_t)par * team + task.team_rank) * 32 + lane], tag | cnt, tag | sum);
-                }
-            } else if (team > 1 || sharded) {
-                // large team: L2 atomics + monotonic arrive counter (3 rotating buffers).  On a sharded chain
-                // the CTA that arrives LAST holds the GPU's totals and sends them to every GPU's mailbox over
-                // NVLink as tagged 64-bit words {iteration | n_k}, {iteration | sum lo}, {iteration | sum hi}.
-                if (warp == lead) {
-                    const int buf = j % 3;
-                    if (cnt != 0u) {
-                        atomicAdd(&ex_cnt[buf * 32 + lane], cnt);
-                        atomicAdd(&ex_sum[buf * 32 + lane], sum);
-                    }
-                    __syncwarp();
-                    unsigned prev = 0;
-                    if (lane == 0) {
-                        __threadfence();
-                        prev = atomicAdd(ex_arrive, 1u);
-                    }
-                    if (sharded) {
-                        prev = __shfl_sync(FULL, prev, 0);
-                        if (prev + 1u == (unsigned)team * (unsigned)(j - j_begin)) {   // the counter starts at 0 every launch
-                            __threadfence();
-                            const unsigned g_c = ld_relaxed_u32(&ex_cnt[buf * 32 + lane]);
-                            const unsigned long long g_s = ld_relaxed_u64(&ex_sum[buf * 32 + lane]);
-                            const unsigned long long tag = (unsigned long long)(unsigned)j << 32;
-                            const size_t slot = (((size_t)par * n_shards + b.shard_rank) * 32 + lane) * 4;
-                            if (own) {
-                                for (int g = 0; g < n_shards; ++g) {
-                                    unsigned long long* const dst = static_cast<unsigned long long*>(b.shard_mailbox[g]) + slot;
-                                    st_relaxed_sys_v2(dst, tag | g_c, tag | (g_s & 0xffffffffull));
-                                    st_relaxed_sys_u64(dst + 2, tag | (g_s >> 32));
-                                }
-                            }
-                        }
-                    }
-                    if (task.team_rank == 0) {             // recycle the buffer last read in j-1
-                        const int old = (j + 2) % 3;
-                        ex_cnt[old * 32 + lane] = 0u;
-                        ex_sum[old * 32 + lane] = 0ull;
-                    }
-                }
-            }
+            if (warp == lead)
+                serial_part<K>(prm, task, j, par, dom, slice_n, slice_t, save, row, rows, key0, key1,
+                               s_stat, s_coef, s_hyp, s_rhb, &s_dom, &s_bad, &s_abort PHASE_LEAD_ARG);
+            __syncthreads();                               // B: coefficients of iteration j + 1 are published
             PHASE_MARK(4);
-            // shape-independent half of the Marsaglia-Tsang trials, overlapped with the exchange
-            TrialRandoms rnd[PASSES][NTRIALS];
-            if (!inject_coef) {
-#pragma unroll
-                for (int p = 0; p < PASSES; ++p) {
-                    const uint32_t purpose = ((HALF ? (lane >> 4) : p) == 0 ? 1u : 2u) + 4u * (uint32_t)comp;
-#pragma unroll
-                    for (int t = 0; t < NTRIALS; ++t)
-                        rnd[p][t] = trial_randoms(philox4x32_10_rk((uint32_t)t, (uint32_t)j, chain_id, purpose, prm.rk));
-                }
-            }
-            // ---- team totals: every warp gathers all members itself -----------------------------
-            unsigned tot_c = cnt;
-            unsigned long long tot_s = sum;
-            if (mailbox) {
-                // lane = component; K <= 16: the upper half-warp takes the odd members.  All loads of a
-                // round are in flight together; a word is valid once it carries this iteration's tag.
-                constexpr int SPLIT = HALF ? 2 : 1;
-                constexpr int ROUND = 16;
-                tot_c = 0;
-                tot_s = 0;
-                if (live) {
-                    const ulonglong2* const base = &mbox[(size_t)par * team * 32 + comp];
-                    for (int m0 = HALF ? (lane >> 4) : 0; m0 < team && !s_abort; m0 += ROUND * SPLIT) {
-                        unsigned pend = 0;
-#pragma unroll
-                        for (int i = 0; i < ROUND; ++i)
-                            if (m0 + i * SPLIT < team) pend |= 1u << i;
-                        while (pend) {
-                            ulonglong2 v[ROUND];
-#pragma unroll
-                            for (int i = 0; i < ROUND; ++i)
-                                if (pend & (1u << i)) v[i] = ld_relaxed_v2(&base[(size_t)(m0 + i * SPLIT) * 32]);
-#pragma unroll
-                            for (int i = 0; i < ROUND; ++i) {
-                                if ((pend & (1u << i)) && (unsigned)(v[i].x >> 32) == (unsigned)j &&
-                                    (unsigned)(v[i].y >> 32) == (unsigned)j) {
-                                    tot_c += (unsigned)v[i].x;
-                                    tot_s += (unsigned)v[i].y;
-                                    pend &= ~(1u << i);
-                                }
-                            }
-                            if (pend && wd.expired(wd_limit)) { s_abort = 1u; break; }
-                        }
-                    }
-                }
-                if constexpr (HALF) {
-                    tot_c += __shfl_xor_sync(FULL, tot_c, 16);
-                    tot_s += __shfl_xor_sync(FULL, tot_s, 16);
-                }
-            } else if (sharded) {
-                // every CTA of every GPU reads the G shards' totals from its GPU's own mailbox
-                const unsigned long long* const mine = static_cast<const unsigned long long*>(b.shard_mailbox[b.shard_rank]);
-                tot_c = 0;
-                tot_s = 0;
-                if (own) {
-                    for (int g = 0; g < n_shards; ++g) {
-                        const unsigned long long* const src = mine + (((size_t)par * n_shards + g) * 32 + lane) * 4;
-                        for (;;) {
-                            const ulonglong2 w01 = ld_relaxed_sys_v2(src);
-                            const unsigned long long w2 = ld_relaxed_sys_u64(src + 2);
-                            if ((unsigned)(w01.x >> 32) == (unsigned)j && (unsigned)(w01.y >> 32) == (unsigned)j &&
-                                (unsigned)(w2 >> 32) == (unsigned)j) {
-                                tot_c += (unsigned)w01.x;
-                                tot_s += (w01.y & 0xffffffffull) | (w2 << 32);
-                                break;
-                            }
-                            if (wd.expired(wd_limit)) { s_abort = 1u; break; }
-                        }
-                        if (s_abort) break;
-                    }
-                }
-            } else if (team > 1) {
-                const int buf = j % 3;
-                const unsigned target = (unsigned)team * (unsigned)(j - j_begin);
-                while (ld_acquire_u32(ex_arrive) < target)
-                    if (wd.expired(wd_limit)) { s_abort = 1u; break; }
-                tot_c = ld_relaxed_u32(&ex_cnt[buf * 32 + lane]);
-                tot_s = ld_relaxed_u64(&ex_sum[buf * 32 + lane]);
-            }
-            PHASE_MARK(5);
-
-            if (trace && warp == lead && task.team_rank == 0 && own) {
-                const size_t o = ((size_t)r * niter + (j - 1)) * kreal + lane;
-                b.trace_nk[o] = (int64_t)tot_c;
-                b.trace_tk[o] = (int64_t)tot_s;
-            }
-            // next iteration skips the most populated label in the atomics
-            {
-                const unsigned keyv = own ? ((tot_c << 5) | (unsigned)(31 - lane)) : 0u;
-                dom = 31 - (int)(__reduce_max_sync(FULL, keyv) & 31u);
-            }
-
-            // ---- posterior update (gibbs.py:210-211): lane = component, every warp the same bits ------
-            if (inject_coef) {
-                ca = make_float2(-INFINITY, 0.0f);
-                if (own && j < j_end) {
-                    const size_t o = ((size_t)r * niter + j) * kreal + lane;
-                    ca = make_float2(b.inj_c[o], b.inj_a[o]);
-                    bad |= !coef_ok(ca);
-                }
-                PHASE_MARK(6);
-            } else {
-                const float fcnt = (float)tot_c;
-                float l2g[PASSES];
-#pragma unroll
-                for (int p = 0; p < PASSES; ++p) {
-                    const float n_c = HALF ? __shfl_sync(FULL, fcnt, comp) : fcnt;
-                    const uint32_t purpose = ((HALF ? (lane >> 4) : p) == 0 ? 1u : 2u) + 4u * (uint32_t)comp;
-                    l2g[p] = log2_gamma<NTRIALS>(hyp[p] + n_c, rnd[p], (uint32_t)j, chain_id, purpose, key0, key1, live);
-                }
-                // log2 of the weight gamma y_k and of the rate r_k = G_k / (b + T_k), for component `lane`
-                const float l2den = __log2f(fmaf((float)tot_s, ts, rh_b));
-                const float l2y = l2g[0];
-                const float l2r = (HALF ? __shfl_down_sync(FULL, l2g[0], 16) : l2g[PASSES - 1]) - l2den;
-                const float rate = fast_exp2(l2r);
-                // The indicator draw is invariant to a common factor of the weights (the inverse CDF is
-                // taken at u * total), so the sweep runs on the UNNORMALISED Dirichlet gammas:
-                // c_k = log2(y_k r_k); the weights are normalised only for the stored rows.
-                ca = own ? make_float2(l2y + l2r, rate * (ts * LOG2E)) : make_float2(-INFINITY, 0.0f);
-                // a usable row: every slope finite and >= 0, every intercept finite or -inf (a dead
-                // component), at least one alive
-                bad |= (own && !coef_ok(ca)) || !__any_sync(FULL, own && ca.x > -INFINITY);
-                PHASE_MARK(6);
-                if (save && warp == lead && task.team_rank == 0 && row < rows) {
-                    const float y = own ? l2y : -INFINITY;
-                    const float mx = warp_max(y);
-                    const float tot = warp_sum(own ? fast_exp2(y - mx) : 0.0f);
-                    if (own) {
-                        const size_t o = ((size_t)r * rows + row) * kreal + lane;
-                        b.mcweights[o] = exp2((double)(y - mx - __log2f(tot)));
-                        b.mcrates[o] = (double)rate;
-                    }
-                }
-            }
-            PHASE_MARK(7);
+            if (s_abort) break;                            // uniform: written before the barrier
         }
         PHASE_FLUSH;
         if (b.task_cycles && tid == 0) b.task_cycles[ti] = busy_cycles;
-        if (b.final_c && b.final_a && task.team_rank == 0 && warp == lead && own) {   // state for a following launch
-            b.final_c[(size_t)r * kreal + lane] = ca.x;
-            b.final_a[(size_t)r * kreal + lane] = ca.y;
+        if (b.final_c && b.final_a && task.team_rank == 0 && tid < kreal) {   // state for a following launch
+            b.final_c[(size_t)r * kreal + tid] = s_coef[tid].x;
+            b.final_a[(size_t)r * kreal + tid] = s_coef[tid].y;
         }
-        if (bad) atomicOr(&s_bad, 1u);
-        __syncthreads();
         if (tid == 0 && s_bad) atomicOr(reinterpret_cast<unsigned*>(&b.status[r]), (unsigned)BRTA_STATUS_NONFINITE);
         if (tid == 0 && s_abort) atomicOr(reinterpret_cast<unsigned*>(&b.status[r]), (unsigned)BRTA_STATUS_TIMEOUT);
         __syncthreads();

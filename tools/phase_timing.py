@@ -38,8 +38,8 @@ e0.record(); eng.launch(db); e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
 ph = buf.cpu().numpy().reshape(-1, 8).astype(np.float64)
 ph = ph[ph.sum(1) > 0]
-names = ['sweep', 'S1 wait', 'partials+post', 'gather', 'S2', 'gamma', 'combine', 'S3']
-tot = ph.sum(1).mean()
+names = ['table build', 'wait C', 'sweep', 'wait A', 'serial+wait B', '(lead) post', '(lead) gather', '(lead) posterior']
+tot = ph[:, :5].sum(1).mean()          # phases 5-7 are the lead warp's view of phase 4
 print(f'{ms:.2f} ms, {db.units / ms / 1e6:.1f} G units/s, grid {db.plan.grid}, teams {db.plan.team_size.min()}-{db.plan.team_size.max()}, '
       f'slice {db.plan.slice_cap_quads} quads; cycles/iter {tot / niter:.0f}')
 for i, nme in enumerate(names):
@@ -57,7 +57,7 @@ try:
             k = costs[int(t['chain'])].served(s0, e0)
             A[bidx] += (k, e0 - s0 - k, 1)
     full = buf.cpu().numpy().reshape(-1, 8).astype(np.float64)
-    y = full[:, 0] / niter
+    y = full[:, 2] / niter
     sel = A[:, 2] > 0
     coef, *_ = np.linalg.lstsq(A[sel], y[sel], rcond=None)
     print(f'sweep cycles/iter ~ {coef[0]:.2f} * served + {coef[1]:.2f} * recomputed + {coef[2]:.0f} * tasks  '
@@ -71,10 +71,10 @@ if db.plan.n_waves == 1:
     spread, wait = [], []
     for r in range(len(chains)):
         ctas = [b for b in range(db.plan.grid) if len(db.plan.tasks_of_cta(b)) and db.plan.tasks_of_cta(b)[0]['chain'] == r]
-        sw = allph[ctas, 0]
+        sw = allph[ctas, 2]
         spread.append((sw.max() - sw.min()) / sw.mean())
         wait.append((sw.max() - sw.mean()))
     print(f'within-team sweep spread (max-min)/mean: median {np.median(spread):.2f}, max {np.max(spread):.2f}; '
           f'mean wait for the slowest member {np.mean(wait):.0f} cyc/iter')
-    tm = np.array([allph[[b for b in range(db.plan.grid) if len(db.plan.tasks_of_cta(b)) and db.plan.tasks_of_cta(b)[0]['chain'] == r], 0].max() for r in range(len(chains))])
+    tm = np.array([allph[[b for b in range(db.plan.grid) if len(db.plan.tasks_of_cta(b)) and db.plan.tasks_of_cta(b)[0]['chain'] == r], 2].max() for r in range(len(chains))])
     print(f'slowest-member sweep per team: min {tm.min():.0f} mean {tm.mean():.0f} max {tm.max():.0f} cyc/iter')
