@@ -36,6 +36,7 @@ FLAG_INJECT_COEF = 2
 FLAG_INJECT_U = 4
 FLAG_TRACE = 8
 FLAG_NO_TABLE = 16
+FLAG_CTAS3 = 32
 
 STATUS_OK = 0
 STATUS_NONFINITE = 1

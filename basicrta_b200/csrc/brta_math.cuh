@@ -81,19 +81,24 @@ struct TrialRandoms {
     float l2_boost;   // log2 of the boost uniform in (0,1] (word 3)
 };
 
+// Every floating-point operation below is spelled out (__fmul_rn / __fadd_rn / __fmaf_rn): the compiler may
+// neither contract a multiply and an add into an FMA nor keep one apart, so every build of the kernel
+// (any K, 3 or 4 CTAs per SM) draws bit-identical variates from the same Philox words.
+constexpr float LN2 = 0.6931471805599453f;
+
 __device__ __forceinline__ TrialRandoms trial_randoms(const Words4& w)
 {
     TrialRandoms r;
     const float u1 = word_to_unit_open_low(w.x);
     const float u2 = word_to_unit(w.y);
     float rad;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-2.0f * __logf(u1)));
-    r.z = rad * __cosf(6.283185307179586f * u2);
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(__fmul_rn(-2.0f * LN2, __log2f(u1))));
+    r.z = __fmul_rn(rad, __cosf(__fmul_rn(6.283185307179586f, u2)));
     r.u = word_to_unit_open(w.z);
-    r.log_u = __logf(r.u);
-    const float z2 = r.z * r.z;
-    r.half_zz = 0.5f * z2;
-    r.squeeze = 1.0f - 0.0331f * z2 * z2;
+    r.log_u = __fmul_rn(LN2, __log2f(r.u));
+    const float z2 = __fmul_rn(r.z, r.z);
+    r.half_zz = __fmul_rn(0.5f, z2);
+    r.squeeze = __fmaf_rn(-0.0331f, __fmul_rn(z2, z2), 1.0f);
     r.l2_boost = __log2f(word_to_unit_open_low(w.w));
     return r;
 }
@@ -108,26 +113,26 @@ struct GammaTrial { float l2g; bool ok; };               // log2(d v), accepted?
 // -- no logarithm, no cancellation; otherwise 1 + x is far from 1 and the plain form is accurate.
 __device__ __forceinline__ GammaTrial trial_finish(float a, const TrialRandoms& r)
 {
-    const float d = a - (1.0f / 3.0f);
-    const float c = rsqrtf(9.0f * d);
-    const float x = c * r.z;
-    const float t = 1.0f + x;
+    const float d = __fadd_rn(a, -1.0f / 3.0f);
+    const float c = rsqrtf(__fmul_rn(9.0f, d));
+    const float x = __fmul_rn(c, r.z);
+    const float t = __fadd_rn(1.0f, x);
     const float l2t = __log2f(t);                         // NaN for t < 0: such trials are rejected
-    const float x2 = x * x;
+    const float x2 = __fmul_rn(x, x);
     float p = 3.0f / 11.0f;
-    p = fmaf(p, x, -3.0f / 10.0f);
-    p = fmaf(p, x, 3.0f / 9.0f);
-    p = fmaf(p, x, -3.0f / 8.0f);
-    p = fmaf(p, x, 3.0f / 7.0f);
-    p = fmaf(p, x, -3.0f / 6.0f);
-    p = fmaf(p, x, 3.0f / 5.0f);
-    p = fmaf(p, x, -3.0f / 4.0f);
-    const float rhs_small = d * (x2 * x2) * p;
-    const float v = t * t * t;
-    const float rhs_large = r.half_zz + d * (1.0f - v + (3.0f * 0.6931471805599453f) * l2t);
+    p = __fmaf_rn(p, x, -3.0f / 10.0f);
+    p = __fmaf_rn(p, x, 3.0f / 9.0f);
+    p = __fmaf_rn(p, x, -3.0f / 8.0f);
+    p = __fmaf_rn(p, x, 3.0f / 7.0f);
+    p = __fmaf_rn(p, x, -3.0f / 6.0f);
+    p = __fmaf_rn(p, x, 3.0f / 5.0f);
+    p = __fmaf_rn(p, x, -3.0f / 4.0f);
+    const float rhs_small = __fmul_rn(__fmul_rn(d, __fmul_rn(x2, x2)), p);
+    const float v = __fmul_rn(__fmul_rn(t, t), t);
+    const float rhs_large = __fmaf_rn(d, __fmaf_rn(3.0f * LN2, l2t, __fadd_rn(1.0f, -v)), r.half_zz);
     const float rhs = fabsf(x) < 0.125f ? rhs_small : rhs_large;
     const bool ok = (t > 0.0f) && (r.u < r.squeeze || r.log_u < rhs);
-    return GammaTrial{__log2f(d) + 3.0f * l2t, ok};
+    return GammaTrial{__fmaf_rn(3.0f, l2t, __log2f(d)), ok};
 }
 
 // log2 of a Gamma(shape, 1) variate: the first accepted trial in counter order 0, 1, 2, ... of the
@@ -136,7 +141,7 @@ template <int NPRE>
 __device__ __forceinline__ float log2_gamma(float shape, const TrialRandoms (&pre)[NPRE], uint32_t iter,
                                             uint32_t chain, uint32_t purpose, uint32_t k0, uint32_t k1, bool live)
 {
-    const float a = shape < 1.0f ? shape + 1.0f : shape;
+    const float a = shape < 1.0f ? __fadd_rn(shape, 1.0f) : shape;
     float l2g = 0.0f, l2b = 0.0f;
     bool ok = false;
 #pragma unroll
@@ -151,7 +156,7 @@ __device__ __forceinline__ float log2_gamma(float shape, const TrialRandoms (&pr
             if (t.ok) { l2g = t.l2g; l2b = r.l2_boost; break; }
         }
     }
-    if (shape < 1.0f) l2g += __fdividef(l2b, shape);
+    if (shape < 1.0f) l2g = __fadd_rn(l2g, __fdividef(l2b, shape));
     return l2g;
 }
 

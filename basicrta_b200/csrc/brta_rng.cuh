@@ -101,11 +101,11 @@ __device__ __forceinline__ float word_to_unit(uint32_t w)
 // (0,1] and (0,1) variants for the posterior draws (24 bits).
 __device__ __forceinline__ float word_to_unit_open_low(uint32_t w)   // (0, 1]
 {
-    return (float)((w >> 8) + 1u) * 5.9604644775390625e-08f;
+    return __fmul_rn((float)((w >> 8) + 1u), 5.9604644775390625e-08f);
 }
 __device__ __forceinline__ float word_to_unit_open(uint32_t w)       // (0, 1)
 {
-    return ((float)(w >> 8) + 0.5f) * 5.9604644775390625e-08f;
+    return __fmul_rn(__fadd_rn((float)(w >> 8), 0.5f), 5.9604644775390625e-08f);
 }
 
 }  // namespace brta

@@ -940,6 +940,7 @@ __device__ BRTA_SERIAL_ATTR void serial_part(const SweepParams& prm, const brta_
             bad = !coef_ok(ca);
         }
     } else {
+        // explicit __f*_rn operations: no contraction freedom, so every build of the kernel gives the same bits
         const float ts = b.ts[r];
         const float fcnt = (float)tot_c;
         float l2g[PASSES];
@@ -947,27 +948,27 @@ __device__ BRTA_SERIAL_ATTR void serial_part(const SweepParams& prm, const brta_
         for (int p = 0; p < PASSES; ++p) {
             const float n_c = HALF ? __shfl_sync(FULL, fcnt, comp) : fcnt;
             const uint32_t purpose = ((HALF ? (lane >> 4) : p) == 0 ? 1u : 2u) + 4u * (uint32_t)comp;
-            l2g[p] = log2_gamma<NTRIALS>(s_hyp[p][lane] + n_c, rnd[p], (uint32_t)j, chain_id, purpose, key0, key1, live);
+            l2g[p] = log2_gamma<NTRIALS>(__fadd_rn(s_hyp[p][lane], n_c), rnd[p], (uint32_t)j, chain_id, purpose, key0, key1, live);
         }
         // log2 of the weight gamma y_k and of the rate r_k = G_k / (b + T_k), for component `lane`
-        const float l2den = __log2f(fmaf((float)tot_s, ts, s_rhb[lane]));
+        const float l2den = __log2f(__fmaf_rn((float)tot_s, ts, s_rhb[lane]));
         const float l2y = l2g[0];
-        const float l2r = (HALF ? __shfl_down_sync(FULL, l2g[0], 16) : l2g[PASSES - 1]) - l2den;
+        const float l2r = __fsub_rn(HALF ? __shfl_down_sync(FULL, l2g[0], 16) : l2g[PASSES - 1], l2den);
         const float rate = fast_exp2(l2r);
         // The indicator draw is invariant to a common factor of the weights (the inverse CDF is
         // taken at u * total), so the sweep runs on the UNNORMALISED Dirichlet gammas:
         // c_k = log2(y_k r_k); the weights are normalised only for the stored rows.
-        if (own) ca = make_float2(l2y + l2r, rate * (ts * LOG2E));
+        if (own) ca = make_float2(__fadd_rn(l2y, l2r), __fmul_rn(rate, __fmul_rn(ts, LOG2E)));
         // a usable row: every slope finite and >= 0, every intercept finite or -inf (a dead
         // component), at least one alive
         bad = (own && !coef_ok(ca)) || !__any_sync(FULL, own && ca.x > -INFINITY);
         if (save && task.team_rank == 0 && row < rows) {
             const float y = own ? l2y : -INFINITY;
             const float mx = warp_max(y);
-            const float tot = warp_sum(own ? fast_exp2(y - mx) : 0.0f);
+            const float tot = warp_sum(own ? fast_exp2(__fsub_rn(y, mx)) : 0.0f);
             if (own) {
                 const size_t o = ((size_t)r * rows + row) * kreal + lane;
-                b.mcweights[o] = exp2((double)(y - mx - __log2f(tot)));
+                b.mcweights[o] = exp2((double)__fsub_rn(__fsub_rn(y, mx), __log2f(tot)));
                 b.mcrates[o] = (double)rate;
             }
         }
@@ -990,8 +991,13 @@ __device__ BRTA_SERIAL_ATTR void serial_part(const SweepParams& prm, const brta_
 // serial part got shorter, but its four copies slowed every co-resident sweep down by 45 %; 0.80x overall.)
 // All of the lead warp's state lives in shared memory between iterations, so the sweep's register
 // allocation carries none of it.
-template <int K, bool EXACT>
-__global__ void __launch_bounds__(THREADS, min_ctas(K))
+//
+// CTAS = co-resident CTAs per SM the register budget is capped for.  K <= 16 is built twice: 4 CTAs (128
+// registers per thread; best when the launch has several waves of work) and 3 CTAs (168 registers, a third
+// more shared memory per slice: fewer, larger slices per chain, i.e. less per-iteration fixed work -- best for
+// small batches, +5-8 % at 50 chains per GPU).  BRTA_FLAG_CTAS3 selects the latter; the host measures both.
+template <int K, bool EXACT, int CTAS = min_ctas(K)>
+__global__ void __launch_bounds__(THREADS, CTAS)
 gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
 {
     // K <= 16: lanes 0..15 draw the Dirichlet gammas, lanes 16..31 the rate gammas of component lane & 15
@@ -1195,7 +1201,19 @@ typedef void (*kernel_fn)(const SweepParams);
 struct Variant {
     int k;
     kernel_fn fast, exact;
-    kernel_fn pick(uint32_t flags) const { return (flags & BRTA_FLAG_EXACT) ? exact : fast; }
+    kernel_fn fast3;                                       // FAST arithmetic at 3 CTAs per SM (nullptr: `fast` already is)
+    kernel_fn pick(uint32_t flags) const
+    {
+        if (flags & BRTA_FLAG_EXACT) return exact;
+        return ((flags & BRTA_FLAG_CTAS3) && fast3) ? fast3 : fast;
+    }
 };
+
+template <int K>
+kernel_fn three_cta_kernel()
+{
+    if constexpr (min_ctas(K) > 3) return gibbs_sweep_kernel<K, false, 3>;
+    else return nullptr;
+}
 
 }  // namespace brta

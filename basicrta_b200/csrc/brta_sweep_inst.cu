@@ -11,7 +11,8 @@
 namespace brta {
 Variant BRTA_CAT(variant_k, BRTA_INST_K)()
 {
-    return Variant{BRTA_INST_K, gibbs_sweep_kernel<BRTA_INST_K, false>, gibbs_sweep_kernel<BRTA_INST_K, true>};
+    return Variant{BRTA_INST_K, gibbs_sweep_kernel<BRTA_INST_K, false>, gibbs_sweep_kernel<BRTA_INST_K, true>,
+                   three_cta_kernel<BRTA_INST_K>()};
 }
 }  // namespace brta
 

@@ -162,11 +162,13 @@ class DeviceBatch:
     executed_ex2_share: float = 1.0                   # ex2 actually executed / units (memoised rows make it < 1)
     segments: list = None                              # iteration ends of the launches of one run (None: one launch)
     cal: tuple = None                                  # (costs, ticks, tick_offset) for re-slicing between segments
+    kernel_choice: dict = None                         # measured choice between the 4- and 3-CTAs-per-SM builds
 
 
 CALIBRATE_MIN_NITER = 2000     # shorter runs are not worth the calibration launches
 CALIBRATE_ITERS = 96           # iterations per calibration launch (the kernel times the second half)
 CALIBRATE_ROUNDS = 2
+CHOICE_ITERS = 384             # iterations of the launches that decide between the two kernel builds
 SEGMENT_MIN_NITER = 20000      # longer calibrated runs are cut into launches and re-sliced in between
 SEGMENT_FRACTIONS = (0.02, 0.06, 0.15, 0.3, 0.5, 0.75)
 SEGMENT_DAMPING = 0.5          # move the boundaries half of the way to the measured optimum (noise, one-segment lag)
@@ -233,6 +235,16 @@ class GibbsEngine:
         return plan
 
     @staticmethod
+    def _check_slice_sums(plan, ticks, tick_offset, d0, n_local):
+        """Per-iteration slice sums are accumulated in 32 bits inside a CTA."""
+        for task in plan.tasks:
+            r = task['chain']
+            lo = tick_offset[r] + 4 * int(task['quad_begin'])
+            hi = min(lo + 4 * int(task['quad_count']), tick_offset[r] + d0 + n_local[r])
+            if int(ticks[lo:hi].sum(dtype=np.int64)) >= (1 << 32):
+                raise ValueError('a slice holds more than 2^32 ticks; use a coarser ts')
+
+    @staticmethod
     def _watchdog_ns(plan, n_data, niter):
         """Rendezvous watchdog of the launch: a CTA may legitimately wait for a team mate that is still
         finishing its previous wave, i.e. up to about the whole run.  Ten times a generous estimate of the
@@ -244,7 +256,7 @@ class GibbsEngine:
 
     # ---- pack + upload -------------------------------------------------------------------
     def prepare(self, chains, ncomp, niter, thin=100, seed=0, flags=0, inject=None, n_waves=None, shard=None,
-                calibrate=None, segments=None):
+                calibrate=None, segments=None, choose_kernel=None):
         """``chains``: list of :class:`ChainInput`.  ``inject``: dict with optional
         ``coef_c``/``coef_a`` (list of [niter,K] float32) and ``u`` (list of [niter,N]).
         ``shard`` (internal, see :func:`run_sharded`): this GPU's part of ONE chain split over
@@ -312,14 +324,6 @@ class GibbsEngine:
             iw = w0 if ch.init_weights is None else ch.init_weights
             ir = r0 if ch.init_rates is None else ch.init_rates
             init_c[r], init_a[r] = coefficients(iw, ir, ch.ts)
-        # per-iteration slice sums are accumulated in 32 bits inside a CTA
-        for task in plan.tasks:
-            r = task['chain']
-            lo = tick_offset[r] + 4 * int(task['quad_begin'])
-            hi = min(lo + 4 * int(task['quad_count']), tick_offset[r] + d0 + n_local[r])
-            if int(ticks[lo:hi].sum(dtype=np.int64)) >= (1 << 32):
-                raise ValueError('a slice holds more than 2^32 ticks; use a coarser ts')
-
         ind_stride = n_local.astype(np.int32)
         ind_bytes = rows * n_local
         ind_offset = np.concatenate(([0], np.cumsum(ind_bytes)[:-1])).astype(np.int64) - d0
@@ -367,6 +371,7 @@ class GibbsEngine:
         b.cta_task_begin = up('cta_task_begin', plan.cta_task_begin)
         b.grid_ctas = plan.grid
         b.slice_cap_quads = plan.smem_units
+        self._check_slice_sums(plan, ticks, tick_offset, d0, n_local)
 
         def dev_zeros(name, shape, dtype):
             T[name] = torch.zeros(shape, dtype=dtype, device=dev)
@@ -414,6 +419,11 @@ class GibbsEngine:
         if calibrate:
             if shard is not None or flags & (_cabi.FLAG_INJECT_COEF | _cabi.FLAG_INJECT_U | _cabi.FLAG_TRACE):
                 raise ValueError('calibration needs a plain (not sharded, not injected, not traced) batch')
+            if choose_kernel is None:
+                choose_kernel = plan.n_waves == 1 and K <= 16 and not flags & (_cabi.FLAG_EXACT | _cabi.FLAG_CTAS3)
+            if choose_kernel:                              # calibrates both candidates itself
+                self._choose_kernel(db, n_data, costs, [int(np.max(ch.ticks)) < 65536 for ch in chains], ticks, tick_offset)
+                plan = db.plan
             # every launch ends with a tail in which CTAs run dry; with several waves that tail is long (the
             # waves are only balanced over the whole run), so only single-wave schedules are segmented by default
             if segments is None and niter >= SEGMENT_MIN_NITER and plan.n_waves == 1:
@@ -427,8 +437,9 @@ class GibbsEngine:
                         T['init_' + name + '0'] = T['init_' + name].clone()
                     b.final_c, b.final_a = T['final_c'].data_ptr(), T['final_a'].data_ptr()
                     db.segments, db.cal = ends, (costs, ticks, tick_offset)
-            for _ in range(CALIBRATE_ROUNDS):
-                self._calibrate(db, costs, ticks, tick_offset)
+            if not choose_kernel:
+                for _ in range(CALIBRATE_ROUNDS):
+                    self._calibrate(db, costs, ticks, tick_offset)
         if shard is None and costs is not None:
             db.executed_ex2_share = self._executed_ex2_share(plan, costs, float(n_data.sum()))
         if shard is not None:
@@ -449,6 +460,85 @@ class GibbsEngine:
                 rows_built = min(cc.rows, hi_tick - int(cc.qmin[s0]) + 1)
             done += 4.0 * (e0 - s0 - k) + rows_built
         return done / n_total
+
+    def _time_short(self, db, iters=CALIBRATE_ITERS, reps=2):
+        """Device time (ms) of a short launch of ``db`` (no row saved, workspace reset afterwards)."""
+        torch = self.torch
+        cal = _cabi.Batch.from_buffer_copy(db.batch)
+        cal.niter, cal.thin = int(iters), int(iters) + 2
+        best = float('inf')
+        with torch.cuda.device(self.device):
+            s = torch.cuda.current_stream()
+            for rep in range(reps + 1):                             # the first launch warms up (module load, L2)
+                self.reset(db)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rc = self.lib.brta_gibbs_run_batch(C.byref(cal), C.c_void_p(s.cuda_stream))
+                e1.record()
+                _cabi.check(rc, 'brta_gibbs_run_batch (kernel choice)')
+                s.synchronize()
+                if rep:
+                    best = min(best, e0.elapsed_time(e1))
+        if int(db.tensors['status'].max().item()) != 0:
+            raise _cabi.BrtaError('short launch failed (status != 0)')
+        self.reset(db)
+        return best
+
+    def _choose_kernel(self, db, n_data, costs, narrow, ticks, tick_offset):
+        """K <= 16 comes in two builds: 4 CTAs per SM at 128 registers, and 3 CTAs per SM at 168 registers
+        with a third more shared memory per slice (BRTA_FLAG_CTAS3).  Fewer, larger slices mean less
+        per-iteration fixed work per chain, which wins when the batch is small (single-wave schedules:
+        +5-8 % at 50 chains per GPU) and loses when the GPU is full of work.  Rather than guess, time a short
+        launch of each -- after the measured slicing of each -- and keep the faster schedule.  Results do not
+        depend on the choice."""
+        torch = self.torch
+        T, H, b = db.tensors, db.host, db.batch
+        for _ in range(CALIBRATE_ROUNDS):
+            self._calibrate(db, costs, ticks, tick_offset)
+        t_base = self._time_short(db, CHOICE_ITERS)
+        base = dict(plan=db.plan, flags=b.flags, tensors={k: T[k] for k in ('tasks', 'cta_task_begin', 'exchange', 'exch_offset')},
+                    host={k: H[k] for k in ('tasks', 'cta_task_begin', 'exch_offset')}, watchdog=b.watchdog_ns)
+        alt_flags = int(b.flags) | _cabi.FLAG_CTAS3
+        try:
+            plan = self._plan(n_data, db.ncomp, alt_flags, costs=costs, narrow=narrow)
+            self._check_slice_sums(plan, ticks, tick_offset, 0, np.asarray(n_data))
+        except (ValueError, _cabi.BrtaError):
+            db.kernel_choice = {'ctas_per_sm': int(base['plan'].grid // self.caps.sm_count), 'ms_4': t_base, 'ms_3': None}
+            return
+        dev = T['tasks'].device
+
+        def up(name, arr):
+            pinned = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+            H[name] = pinned
+            T[name] = pinned.to(dev, non_blocking=True)
+            return T[name].data_ptr()
+
+        exch_size = np.array([(max(_cabi.exch_bytes(int(c)), 1280) + 127) // 128 * 128 for c in plan.team_size], dtype=np.int64)
+        b.flags = alt_flags
+        b.tasks = up('tasks', plan.tasks.view(np.int32).reshape(-1, 6))
+        b.cta_task_begin = up('cta_task_begin', plan.cta_task_begin)
+        b.exch_offset = up('exch_offset', np.concatenate(([0], np.cumsum(exch_size)[:-1])).astype(np.int64))
+        T['exchange'] = torch.zeros(int(exch_size.sum()), dtype=torch.uint8, device=dev)
+        b.exchange = T['exchange'].data_ptr()
+        b.grid_ctas, b.slice_cap_quads = plan.grid, plan.smem_units
+        b.watchdog_ns = self._watchdog_ns(plan, n_data, db.niter)
+        db.plan, db.flags = plan, alt_flags
+        torch.cuda.current_stream(dev).synchronize()
+        if plan.n_waves == 1:
+            for _ in range(CALIBRATE_ROUNDS):
+                self._calibrate(db, costs, ticks, tick_offset)
+            t_alt = self._time_short(db, CHOICE_ITERS)
+        else:
+            t_alt = float('inf')
+        db.kernel_choice = {'ms_4': t_base, 'ms_3': t_alt, 'ctas_per_sm': 3 if t_alt < t_base else 4}
+        if t_alt >= t_base:                                          # keep the 4-CTA schedule
+            T.update(base['tensors'])
+            H.update(base['host'])
+            b.flags, b.watchdog_ns = base['flags'], base['watchdog']
+            b.tasks, b.cta_task_begin = T['tasks'].data_ptr(), T['cta_task_begin'].data_ptr()
+            b.exchange, b.exch_offset = T['exchange'].data_ptr(), T['exch_offset'].data_ptr()
+            db.plan, db.flags = base['plan'], int(base['flags'])
+            b.grid_ctas, b.slice_cap_quads = db.plan.grid, db.plan.smem_units
 
     def _measure(self, db, iters):
         """Cycles per task from the start of an iteration to the post of its partials (a short launch
@@ -640,6 +730,25 @@ class GibbsEngine:
         for name, dst in host_out.items():
             dst.copy_(db.tensors[name], non_blocking=True)
             n += dst.numel() * dst.element_size()
+        return n
+
+    def download_through_ring(self, db):
+        """D2H of every result through the ring of pinned staging buffers (async on the current stream; the
+        bytes are not kept): what a batch too large for one pinned host buffer costs to bring home.
+        Returns bytes."""
+        torch = self.torch
+        ring = self._ring()
+        flat = db.tensors['indicator']
+        n = 0
+        for k, a in enumerate(range(0, int(flat.numel()), self.STREAM_CHUNK_BYTES)):
+            b = min(a + self.STREAM_CHUNK_BYTES, int(flat.numel()))
+            ring[k % len(ring)][:b - a].copy_(flat[a:b], non_blocking=True)
+            n += b - a
+        for name in ('mcweights', 'mcrates', 'status'):
+            t = db.tensors[name]
+            nb = t.numel() * t.element_size()
+            ring[0][:nb].view(t.dtype).copy_(t.reshape(-1), non_blocking=True)
+            n += nb
         return n
 
     def results_from_host(self, db, host_out):
@@ -902,11 +1011,12 @@ class ShardedChain:
         self.niter = int(niter)
         self._launches = 0
 
-    def launch(self):
+    def launch(self, before=None, after=None):
         """Enqueue this rank's kernel.  The G kernels wait for each other on the device, so every rank must
         call it (a host barrier first keeps a late rank from eating into the watchdog).  The mailbox tags
         are iteration numbers, so a re-run first zeroes the mailboxes (between two barriers: no rank may
-        still be reading, none may already be writing)."""
+        still be reading, none may already be writing).  ``before`` / ``after`` are called right around
+        the launch itself (after the barriers), e.g. to record timing events on the stream."""
         torch = self.torch
         torch.cuda.synchronize(self.device)
         if self._launches:
@@ -919,7 +1029,13 @@ class ShardedChain:
             torch.cuda.synchronize(self.device)
         self._launches += 1
         self.dist.barrier(group=self.group)
-        self.engine.launch(self.db)
+        torch.cuda.synchronize(self.device)                          # the barrier's own kernel is done
+        with torch.cuda.device(self.device):
+            if before is not None:
+                before()
+            self.engine.launch(self.db)
+            if after is not None:
+                after()
 
     def fetch(self):
         return self.engine.fetch(self.db)[0]

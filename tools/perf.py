@@ -43,7 +43,6 @@ ov = os.environ.get('BRTA_OVERHEAD')
 eng = GibbsEngine(0, ctas_per_sm=int(cps) if cps else None, overhead_quads=float(ov) if ov else None)
 db = eng.prepare(chains, 15, niter, thin=100, seed=1, n_waves=int(nw) if nw else None, calibrate=bool(int(os.environ.get('BRTA_CALIBRATE', '0'))),
                  flags=_cabi.FLAG_NO_TABLE if 'notable' in sys.argv else 0)
-p = db.plan
 best = 1e30
 for rep in range(3):
     eng.reset(db)
@@ -51,6 +50,7 @@ for rep in range(3):
     e0.record(); eng.launch(db); e1.record(); torch.cuda.synchronize()
     best = min(best, e0.elapsed_time(e1))
 st = db.tensors['status'].cpu().numpy()
+p = db.plan
 print(f'chains {n_chains} niter {niter}: {best:8.2f} ms  {db.units / best / 1e6:8.1f} G units/s  '
       f'grid {p.grid}, waves {p.n_waves}, teams {p.team_size.min()}-{p.team_size.max()}, '
-      f'slice {p.slice_cap_quads} quads, plan eff {p.est_efficiency:.3f}, status max {int(st.max())}')
+      f'slice {p.slice_cap_quads} quads, plan eff {p.est_efficiency:.3f}, status max {int(st.max())}, choice {db.kernel_choice}')
