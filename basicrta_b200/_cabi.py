@@ -16,7 +16,8 @@ INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
 ABI_VERSION = 4
 THREADS = 128
-MAX_NCOMP = 32
+MAX_NCOMP = 255
+LANE_MAX_NCOMP = 32
 TICK_LIMIT = 1 << 23
 MAILBOX_MAX_TEAM = 32
 MAX_SHARDS = 16
@@ -110,7 +111,8 @@ def build(force=False, verbose=False, extra_flags=(), lib_path=None, ncomps=SWEE
     lib_path = lib_path or LIB_PATH
     tag = ('_' + str(abs(hash(tuple(extra_flags))) % 10 ** 8)) if extra_flags else ''
     units = [('host' + tag, os.path.join(CSRC, 'brta_gibbs.cu'), []),
-             ('pindicator' + tag, os.path.join(CSRC, 'brta_pindicator.cu'), [])]
+             ('pindicator' + tag, os.path.join(CSRC, 'brta_pindicator.cu'), []),
+             ('wide' + tag, os.path.join(CSRC, 'brta_wide.cu'), [])]
     units += [(f'sweep_k{k}' + tag, os.path.join(CSRC, 'brta_sweep_inst.cu'), [f'-DBRTA_INST_K={k}']) for k in ncomps]
     objs = [os.path.join(OBJ_DIR, name + '.o') for name, _, _ in units]
     if not force and _newer(lib_path, HEADERS + [u[1] for u in units]):

@@ -85,6 +85,10 @@ const Variant* pick_variant(int ncomp)
     return nullptr;
 }
 
+// brta_wide.cu: 32 < ncomp <= 255
+int launch_wide(const brta_batch& b, cudaStream_t stream);
+int wide_launch_info(uint32_t flags, brta_launch_info* info);
+
 // the ABI never leaves the calling thread on another device
 struct DeviceGuard {
     int prev = -1;
@@ -130,8 +134,15 @@ int brta_gibbs_launch_info(int device, int ncomp, uint32_t flags, int slice_cap_
                            brta_launch_info* info)
 {
     if (!info) return brta::fail(BRTA_E_NULL, "brta_gibbs_launch_info: info is NULL");
+    if (ncomp < 1 || ncomp > BRTA_MAX_NCOMP) return brta::fail(BRTA_E_NCOMP, "ncomp must be in 1..255");
+    if (ncomp > BRTA_LANE_MAX_NCOMP) {
+        brta::DeviceGuard guard(device);
+        if (guard.err != cudaSuccess) return brta::cuda_fail(guard.err, "cudaSetDevice");
+        info->kernel_ncomp = ncomp;
+        return brta::wide_launch_info(flags, info);
+    }
     const brta::Variant* v = brta::pick_variant(ncomp);
-    if (ncomp < 1 || !v) return brta::fail(BRTA_E_NCOMP, "ncomp must be in 1..32");
+    if (!v) return brta::fail(BRTA_E_NCOMP, "ncomp must be in 1..255");
     brta::kernel_fn fn = v->pick(flags);
     brta::DeviceGuard guard(device);
     cudaError_t e = guard.err;
@@ -156,9 +167,11 @@ int brta_gibbs_run_batch(const brta_batch* batch, void* stream)
 {
     if (!batch) return brta::fail(BRTA_E_NULL, "brta_gibbs_run_batch: batch is NULL");
     const brta_batch& b = *batch;
-    const brta::Variant* v = brta::pick_variant(b.ncomp);
-    if (b.ncomp < 1 || !v) return brta::fail(BRTA_E_NCOMP, "ncomp must be in 1..32");
-    if (b.n_chains < 1 || b.niter < 1 || b.thin < 1 || b.grid_ctas < 1 || b.slice_cap_quads < 1)
+    if (b.ncomp < 1 || b.ncomp > BRTA_MAX_NCOMP) return brta::fail(BRTA_E_NCOMP, "ncomp must be in 1..255");
+    const bool wide = b.ncomp > BRTA_LANE_MAX_NCOMP;       // one CTA per chain, no schedule
+    const brta::Variant* v = wide ? nullptr : brta::pick_variant(b.ncomp);
+    if (!wide && !v) return brta::fail(BRTA_E_NCOMP, "ncomp must be in 1..255");
+    if (b.n_chains < 1 || b.niter < 1 || b.thin < 1 || (!wide && (b.grid_ctas < 1 || b.slice_cap_quads < 1)))
         return brta::fail(BRTA_E_RANGE, "n_chains, niter, thin, grid_ctas, slice_cap_quads must be >= 1");
     if (b.iter_begin < 0 || b.iter_end < 0 || b.iter_end > b.niter ||
         b.iter_begin >= (b.iter_end > 0 ? b.iter_end : b.niter))
@@ -167,8 +180,8 @@ int brta_gibbs_run_batch(const brta_batch* batch, void* stream)
         return brta::fail(BRTA_E_RANGE, "tick_bytes must be 2 or 4");
     if (!b.max_tick) return brta::fail(BRTA_E_NULL, "max_tick is required");
     if (!b.ticks || !b.tick_offset || !b.n_data || !b.chain_id || !b.ts || !b.whyper || !b.rhyper ||
-        !b.indicator || !b.ind_offset || !b.ind_stride || !b.status || !b.tasks ||
-        !b.cta_task_begin || !b.exchange || !b.exch_offset)
+        !b.indicator || !b.ind_offset || !b.ind_stride || !b.status ||
+        (!wide && (!b.tasks || !b.cta_task_begin || !b.exchange || !b.exch_offset)))
         return brta::fail(BRTA_E_NULL, "brta_gibbs_run_batch: a required pointer is NULL");
     if (b.flags & BRTA_FLAG_INJECT_COEF) {
         if (!b.inj_c || !b.inj_a) return brta::fail(BRTA_E_NULL, "INJECT_COEF needs inj_c and inj_a");
@@ -186,12 +199,13 @@ int brta_gibbs_run_batch(const brta_batch* batch, void* stream)
     if ((b.flags & BRTA_FLAG_TRACE) && (!b.trace_nk || !b.trace_tk))
         return brta::fail(BRTA_E_NULL, "TRACE needs trace_nk and trace_tk");
 
-    brta::kernel_fn fn = v->pick(b.flags);
-    const size_t smem = (size_t)b.slice_cap_quads * 16;
     int device = b.device;
     if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return brta::fail(BRTA_E_DEVICE, "no current CUDA device");
     brta::DeviceGuard guard(device);
     if (guard.err != cudaSuccess) return brta::cuda_fail(guard.err, "cudaSetDevice");
+    if (wide) return brta::launch_wide(b, (cudaStream_t)stream);
+    brta::kernel_fn fn = v->pick(b.flags);
+    const size_t smem = (size_t)b.slice_cap_quads * 16;
     cudaError_t e = cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return brta::cuda_fail(e, "cudaFuncSetAttribute(smem)");
     brta::SweepParams prm;

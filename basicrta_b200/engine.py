@@ -235,6 +235,21 @@ class GibbsEngine:
         return plan
 
     @staticmethod
+    def _wide_plan(n_data):
+        """ncomp > 32: the general kernel runs one CTA per chain and needs no schedule; this is the trivial plan
+        the rest of the host code reads (one task per chain, teams of one, one wave)."""
+        from .plan import Plan, TASK_DTYPE
+        n_quads = (np.asarray(n_data, dtype=np.int64) + 3) // 4
+        R = len(n_quads)
+        tasks = np.zeros(R, dtype=TASK_DTYPE)
+        tasks['chain'], tasks['team_size'], tasks['quad_count'], tasks['order'] = np.arange(R), 1, n_quads, np.arange(R)
+        plan = Plan(tasks=tasks, cta_task_begin=np.arange(R + 1, dtype=np.int32), grid=R,
+                    slice_cap_quads=int(n_quads.max()), n_waves=1, team_size=np.ones(R, dtype=np.int32),
+                    wave_of_chain=np.zeros(R, dtype=np.int32), est_efficiency=1.0, smem_units=1)
+        plan.cap_quads, plan.cap_units, plan.tick_total = n_quads.copy(), int(n_quads.max()), {}
+        return plan
+
+    @staticmethod
     def _check_slice_sums(plan, ticks, tick_offset, d0, n_local):
         """Per-iteration slice sums are accumulated in 32 bits inside a CTA."""
         for task in plan.tasks:
@@ -285,6 +300,9 @@ class GibbsEngine:
 
         # canonical order: ascending ticks (stable).  Philox word p belongs to canonical position p.
         order = [_canonical_order(ch.ticks) for ch in chains]
+        wide = K > _cabi.LANE_MAX_NCOMP                    # the general kernel: one CTA per chain, no schedule
+        if wide and (shard is not None or flags & _cabi.FLAG_CTAS3):
+            raise ValueError(f'ncomp > {_cabi.LANE_MAX_NCOMP} supports neither sharded chains nor FLAG_CTAS3')
         if shard is not None:
             if R != 1:
                 raise ValueError('a sharded launch holds exactly one chain')
@@ -297,10 +315,13 @@ class GibbsEngine:
             d0 = 0
             n_local = n_data
             costs = None
-            if not flags & _cabi.FLAG_NO_TABLE:
-                costs = [ChainCost(np.asarray(ch.ticks)[o], K) for ch, o in zip(chains, order)]
-            plan = self._plan(n_data, K, flags, n_waves=n_waves, costs=costs,
-                              narrow=[int(np.max(ch.ticks)) < 65536 for ch in chains])
+            if wide:
+                plan = self._wide_plan(n_data)
+            else:
+                if not flags & _cabi.FLAG_NO_TABLE:
+                    costs = [ChainCost(np.asarray(ch.ticks)[o], K) for ch, o in zip(chains, order)]
+                plan = self._plan(n_data, K, flags, n_waves=n_waves, costs=costs,
+                                  narrow=[int(np.max(ch.ticks)) < 65536 for ch in chains])
         if int(plan.team_size.max()) * int(niter) >= (1 << 31):
             raise ValueError('team_size * niter overflows the arrive counter')
 
@@ -371,7 +392,8 @@ class GibbsEngine:
         b.cta_task_begin = up('cta_task_begin', plan.cta_task_begin)
         b.grid_ctas = plan.grid
         b.slice_cap_quads = plan.smem_units
-        self._check_slice_sums(plan, ticks, tick_offset, d0, n_local)
+        if not wide:                                       # the general kernel sums ticks in 64 bits
+            self._check_slice_sums(plan, ticks, tick_offset, d0, n_local)
 
         def dev_zeros(name, shape, dtype):
             T[name] = torch.zeros(shape, dtype=dtype, device=dev)
@@ -413,6 +435,10 @@ class GibbsEngine:
         db = DeviceBatch(batch=b, plan=plan, tensors=T, host=H, order=order, n_data=n_data, ind_offset=ind_offset,
                          rows=rows, ncomp=K, niter=int(niter), flags=int(flags), h2d_bytes=h2d,
                          units=float(n_data.sum()) * K * int(niter))
+        if wide:
+            if calibrate:
+                raise ValueError(f'ncomp > {_cabi.LANE_MAX_NCOMP} has no schedule to calibrate')
+            calibrate, db.executed_ex2_share = False, 3.0   # three passes over the components per datum
         if calibrate is None:
             calibrate = (shard is None and niter >= CALIBRATE_MIN_NITER and int(plan.team_size.max()) > 1 and
                          not flags & (_cabi.FLAG_INJECT_COEF | _cabi.FLAG_INJECT_U | _cabi.FLAG_TRACE))

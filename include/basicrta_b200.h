@@ -32,7 +32,9 @@ extern "C" {
 #ifndef BRTA_THREADS
 #define BRTA_THREADS          128   /* threads per CTA                                  */
 #endif
-#define BRTA_MAX_NCOMP         32   /* K <= 32 (one warp lane per component)            */
+#define BRTA_MAX_NCOMP        255   /* labels are uint8 (gibbs.py:167-168)              */
+#define BRTA_LANE_MAX_NCOMP    32   /* up to here: the team kernel (one warp lane per component); wider mixtures run
+                                       one CTA per chain through a general, slower kernel (no schedule, no sharding) */
 #define BRTA_TICK_LIMIT  (1u << 23) /* ticks must be < 2^23 (exact in float32)          */
 #define BRTA_MAILBOX_MAX_TEAM   32   /* teams up to this size exchange through tagged mailboxes */
 /* bytes of exchange workspace of a chain run by `team` CTAs (zeroed by the caller):

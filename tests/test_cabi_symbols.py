@@ -54,6 +54,7 @@ def test_constants_match_header():
         return re.search(r'#define\s+%s\s+\(?([0-9a-fx]+)u?' % name, HEADER).group(1)
     assert int(macro('BRTA_THREADS')) == _cabi.THREADS
     assert int(macro('BRTA_MAX_NCOMP')) == _cabi.MAX_NCOMP
+    assert int(macro('BRTA_LANE_MAX_NCOMP')) == _cabi.LANE_MAX_NCOMP
     assert int(macro('BRTA_MAILBOX_MAX_TEAM')) == _cabi.MAILBOX_MAX_TEAM
     for flag in ('EXACT', 'INJECT_COEF', 'INJECT_U', 'TRACE', 'NO_TABLE', 'CTAS3'):
         assert int(macro('BRTA_FLAG_' + flag)) == getattr(_cabi, 'FLAG_' + flag)
@@ -67,7 +68,7 @@ def test_argument_errors_do_not_need_a_gpu():
     assert lib.brta_gibbs_run_batch(None, None) == -1                     # BRTA_E_NULL
     assert b'NULL' in lib.brta_last_error()
     b = _cabi.Batch()
-    b.ncomp = 99
+    b.ncomp = 256
     assert lib.brta_gibbs_run_batch(C.byref(b), None) == -2               # BRTA_E_NCOMP
     assert lib.brta_query(0, None) == -1
     assert lib.brta_pindicator_counts(None, 0, 0, 0, None, 1, 1, None, None) == -1
