@@ -323,10 +323,17 @@ def run_batch(gibbs_list, device=None, seed=None, prepared=False, engine=None, s
             seed = getattr(first, 'seed', None)
         if seed is None:
             seed = _fresh_seed()
-        db = eng.prepare(inputs, first.ncomp, first.niter, thin=first.g, seed=seed)
+        nvtx = eng.torch.cuda.nvtx                             # ranges for nsys / ncu timelines
+        nvtx.range_push(f'brta prepare {len(members)} residues')
+        try:
+            db = eng.prepare(inputs, first.ncomp, first.niter, thin=first.g, seed=seed)
+        finally:
+            nvtx.range_pop()
         if progress is not None:
             progress(0, first.niter)
+        nvtx.range_push('brta sweep')
         eng.launch(db)
+        nvtx.range_pop()
         lock = threading.Lock()
 
         def on_chain(r, res):

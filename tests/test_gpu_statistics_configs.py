@@ -152,8 +152,10 @@ def test_clustered_tau_conditioned_on_cluster_count(runs):
     """End of the pipeline: process_gibbs (host GaussianMixture with n_init = 117, restated plot-free from
     gibbs.py:221-308) on device chains, compared with the reference's own process_gibbs results of the runs
     that found the SAME number of clusters: the median of the slowest cluster's tau samples within 2 %, and
-    the reported tau (the mode of a 15-bin histogram, gibbs.py:691-715 -- its resolution is one bin) within
-    max(2 %, one bin width); the 95 % intervals overlap."""
+    the reported tau within max(2 %, two bin widths) of a reference run's -- it is the mode of a 15-bin
+    histogram (gibbs.py:691-715), so each of the two estimates is only resolved to one bin (2-9 % of tau on
+    these residues; the reference's own runs with equal cluster count scatter by 1.6 bins); the 95 %
+    intervals overlap."""
     from basicrta_b200.gibbs import Gibbs
     kind, K, gold, got = runs
     matched = 0
@@ -179,7 +181,7 @@ def test_clustered_tau_conditioned_on_cluster_count(runs):
             ref_median = np.mean([y['tau_median'] for y in same])
             assert abs(np.median(taus) / ref_median - 1) < REL_TOL, (kind, r, np.median(taus), ref_median)
             best = min(same, key=lambda y: abs(y['tau'][1] - tau))
-            assert abs(tau / best['tau'][1] - 1) < max(REL_TOL, best['tau_binwidth'] / best['tau'][1]), \
+            assert abs(tau / best['tau'][1] - 1) < max(REL_TOL, 2 * best['tau_binwidth'] / best['tau'][1]), \
                 (kind, r, tau, [y['tau'][1] for y in same])
             assert lo < best['tau'][2] and best['tau'][0] < hi
     assert matched >= len(got), matched                        # at least one match per residue on average
