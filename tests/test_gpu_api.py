@@ -84,6 +84,30 @@ def test_parallel_gibbs_runs_residues(tmp_path, monkeypatch):
     assert [g.residue for g in only] == ['X102']
 
 
+def test_dispatch_over_all_gpus_equals_one_gpu(tmp_path, monkeypatch):
+    """``dispatch`` (what ParallelGibbs.run calls) shards residues over GPUs with one host thread per GPU.
+    With a fixed seed the result must not depend on the number of GPUs: chains are keyed by residue name.
+    Runs on however many GPUs the box has (1: the threads path with a single shard)."""
+    import torch
+    from basicrta_b200.gibbs import dispatch
+    monkeypatch.chdir(tmp_path)
+    n_gpu = torch.cuda.device_count()
+    rng = np.random.default_rng(5)
+    times = [np.ceil(rng.exponential(1.5, n) / 0.1) * 0.1 for n in (4000, 1500, 9000, 700, 2500, 6000, 30, 12000)]
+
+    def make():
+        return [Gibbs(t, f'R{i}', 0, ncomp=5, niter=600, cutoff=3.5) for i, t in enumerate(times)]
+    one, many = make(), make()
+    dispatch(one, 1, seed=77, save=False)
+    dispatch(many, n_gpu, seed=77, save=True)
+    assert {g.loc for g in many} == set(range(min(n_gpu, len(times))))       # every GPU got residues
+    for a, b in zip(one, many):
+        np.testing.assert_array_equal(a.mcweights, b.mcweights)
+        np.testing.assert_array_equal(a.mcrates, b.mcrates)
+        np.testing.assert_array_equal(a.indicator, b.indicator)
+        assert os.path.exists(f'basicrta-3.5/{b.residue}/gibbs_600.pkl')
+
+
 @pytest.mark.parametrize('n', [1, 2, 3, 5, 127, 129, 513])
 def test_ragged_sizes_exact(engine, n):
     """N not a multiple of 4 / smaller than a CTA: padding must never be counted."""
@@ -145,7 +169,7 @@ def test_large_team_atomics_path_exact(engine):
 
 def test_argument_validation(engine):
     with pytest.raises(ValueError):
-        engine.prepare([ChainInput(ticks=np.array([1, 2, 3]), ts=0.1)], 33, 10)
+        engine.prepare([ChainInput(ticks=np.array([1, 2, 3]), ts=0.1)], 256, 10)
     with pytest.raises(ValueError):
         engine.prepare([ChainInput(ticks=np.array([], dtype=np.int64), ts=0.1)], 3, 10)
     with pytest.raises(ValueError):
@@ -183,6 +207,46 @@ def test_chain_sharded_over_two_gpus_is_bit_exact():
     assert two.status == 0
     assert np.array_equal(one.mcrates, two.mcrates) and np.array_equal(one.mcweights, two.mcweights)
     assert np.array_equal(one.indicator, two.indicator)
+
+
+def _sharded_rank(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    from basicrta_b200.engine import run_sharded_dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    ticks = O.to_ticks(O.synth_times(80003, [0.9, 0.09, 0.01], [5, 0.05, 0.001], seed=4), 0.1)
+    res, (a, b), order = run_sharded_dist(ChainInput(ticks=ticks, ts=0.1, chain_id=2), 15, 300, thin=50, seed=9, device=rank)
+    np.savez(os.path.join(out_dir, f'rank{rank}.npz'), w=res.mcweights, r=res.mcrates, ind=res.indicator,
+             span=np.array([a, b]), order=order, status=res.status)
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not _two_gpus(), reason='needs 2 GPUs (gpurun --gpus 2)')
+def test_chain_sharded_over_two_processes_is_bit_exact(tmp_path):
+    """The same with ONE PROCESS PER GPU (how torchrun launches bench.py): mailboxes exchanged as CUDA IPC
+    handles by one all_gather, then the ranks only meet inside the kernels.  Every rank's shard of the labels
+    and its copy of the weights / rates must equal the single-GPU run."""
+    import socket
+    import torch.multiprocessing as mp
+    from basicrta_b200.engine import get_engine
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    mp.spawn(_sharded_rank, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    ticks = O.to_ticks(O.synth_times(80003, [0.9, 0.09, 0.01], [5, 0.05, 0.001], seed=4), 0.1)
+    one = get_engine(0).run([ChainInput(ticks=ticks, ts=0.1, chain_id=2)], 15, 300, thin=50, seed=9)[0]
+    covered = 0
+    for rank in range(2):
+        z = np.load(tmp_path / f'rank{rank}.npz')
+        assert int(z['status']) == 0
+        a, b = z['span']
+        np.testing.assert_array_equal(z['w'], one.mcweights)
+        np.testing.assert_array_equal(z['r'], one.mcrates)
+        np.testing.assert_array_equal(z['ind'], one.indicator[:, z['order']][:, a:b])
+        covered += b - a
+    assert covered == len(ticks)
 
 
 def test_full_size_batch_invariants(engine):
