@@ -771,10 +771,11 @@ class GibbsEngine:
             ring[k % len(ring)][:b - a].copy_(flat[a:b], non_blocking=True)
             n += b - a
         for name in ('mcweights', 'mcrates', 'status'):
-            t = db.tensors[name]
-            nb = t.numel() * t.element_size()
-            ring[0][:nb].view(t.dtype).copy_(t.reshape(-1), non_blocking=True)
-            n += nb
+            raw = db.tensors[name].reshape(-1).view(torch.uint8)
+            for k, a in enumerate(range(0, int(raw.numel()), self.STREAM_CHUNK_BYTES)):
+                b = min(a + self.STREAM_CHUNK_BYTES, int(raw.numel()))
+                ring[k % len(ring)][:b - a].copy_(raw[a:b], non_blocking=True)
+            n += int(raw.numel())
         return n
 
     def results_from_host(self, db, host_out):

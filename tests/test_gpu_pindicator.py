@@ -79,3 +79,34 @@ def test_cluster_on_device_equals_cluster_on_host(tmp_path, monkeypatch):
     g.cluster(n_components=3, n_init=3, random_state=0, device=0)
     np.testing.assert_array_equal(g.processed_results.indicator, host)
     assert np.allclose(np.nansum(host, axis=1)[~np.isnan(host).any(axis=1)], 1.0)
+
+
+def test_labels_kept_on_the_device_reduce_to_the_same_counts(tmp_path, monkeypatch):
+    """SURVEY.md 8 f-1 end to end: ``run(keep_indicator_on_device=True)`` leaves the label rows in HBM (the
+    pickle holds ``indicator = None``, which the reference's ``cluster`` understands, gibbs.py:259-262);
+    ``process_gibbs`` then reduces them with brta_pindicator_counts and only [N, clusters] integers cross
+    PCIe.  Same seed => same chain, so the result must equal the host loop on the downloaded labels."""
+    import pickle
+    from basicrta_b200.gibbs import Gibbs
+    from oracle import gibbs_oracle as O
+    monkeypatch.chdir(tmp_path)
+    times = O.synth_times(6000, [0.8, 0.15, 0.05], [4.0, 0.1, 0.003], seed=5)
+
+    def make(name):
+        g = Gibbs(times, name, 0, ncomp=8, niter=6000, cutoff=7.0)
+        g.burnin, g.seed = 2000, 23
+        return g
+    host = make('H1')
+    host.run()
+    dev = make('H1')                                           # same residue name => same Philox chain id
+    dev.run(keep_indicator_on_device=True)
+    assert dev.indicator is None and dev.device_indicator() is not None
+    assert tuple(dev.device_indicator().shape) == (60, 6000) and dev.device_indicator().is_cuda
+    np.testing.assert_array_equal(dev.device_indicator().cpu().numpy(), host.indicator)
+    with open('basicrta-7.0/H1/gibbs_6000.pkl', 'rb') as f:
+        from basicrta_b200.gibbs import load_reference_pickle
+        assert load_reference_pickle(f).indicator is None      # the pickle does not carry the labels
+    host.cluster(n_components=3, n_init=3, random_state=0)
+    dev.cluster(n_components=3, n_init=3, random_state=0)       # picks the resident rows up by itself
+    np.testing.assert_array_equal(dev.processed_results.indicator, host.processed_results.indicator)
+    np.testing.assert_array_equal(dev.processed_results.labels, host.processed_results.labels)

@@ -41,7 +41,9 @@ cps = os.environ.get('BRTA_CTAS_PER_SM')
 nw = os.environ.get('BRTA_WAVES')
 ov = os.environ.get('BRTA_OVERHEAD')
 eng = GibbsEngine(0, ctas_per_sm=int(cps) if cps else None, overhead_quads=float(ov) if ov else None)
+seg = os.environ.get('BRTA_SEGMENTS')
 db = eng.prepare(chains, 15, niter, thin=100, seed=1, n_waves=int(nw) if nw else None, calibrate=bool(int(os.environ.get('BRTA_CALIBRATE', '0'))),
+                 segments=tuple(float(x) for x in seg.split(',')) if seg else None,
                  flags=_cabi.FLAG_NO_TABLE if 'notable' in sys.argv else 0)
 best = 1e30
 for rep in range(3):
