@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, 'csrc')
 OBJ_DIR = os.path.join(CSRC, '_obj')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 THREADS = 128
 MAX_NCOMP = 255
 LANE_MAX_NCOMP = 32
@@ -83,7 +83,7 @@ class Batch(C.Structure):
         ('exchange', C.c_void_p), ('exch_offset', C.c_void_p),
         ('task_cycles', C.c_void_p),
         ('iter_begin', C.c_int32), ('iter_end', C.c_int32), ('final_c', C.c_void_p), ('final_a', C.c_void_p),
-        ('watchdog_ns', C.c_uint64), ('device', C.c_int32), ('reserved0', C.c_int32),
+        ('watchdog_ns', C.c_uint64), ('device', C.c_int32), ('progress_rows', C.c_int32), ('progress', C.c_void_p),
     ]
 
 

@@ -788,6 +788,13 @@ __device__ BRTA_SERIAL_ATTR void serial_part(const SweepParams& prm, const brta_
         const unsigned os = __reduce_add_sync(FULL, (unsigned)sum);
         if (lane == dom) { cnt = slice_n - oc; sum = (unsigned)(slice_t - os); }
     }
+    // Live progress (brta_batch.progress): the rows saved up to iteration j - 1 are published to the host once
+    // every member's stores are visible system-wide.  Member side: a system fence before this iteration's post
+    // (the label stores of the CTA's other threads precede it through barrier A); the publishing side follows
+    // the gather below.
+    const bool publish = b.progress_rows > 0 && b.progress != nullptr && j > 1 &&
+                         (j - 1) % (b.thin * b.progress_rows) == 0;
+    if (publish) __threadfence_system();
     Watchdog wd;
     if (mailbox) {
         if (own) {
@@ -915,6 +922,11 @@ __device__ BRTA_SERIAL_ATTR void serial_part(const SweepParams& prm, const brta_
     if (__any_sync(FULL, abort)) {                         // rendezvous watchdog: give the chain up
         if (lane == 0) *s_abort = 1u;
         return;
+    }
+    if (publish && task.team_rank == 0) {                  // every member has posted iteration j: rows <= (j-1)/thin are complete
+        __threadfence_system();
+        if (lane == 0)
+            asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(b.progress + r), "r"((unsigned)((j - 1) / b.thin)) : "memory");
     }
     PHASE_LEAD_MARK(6);
 

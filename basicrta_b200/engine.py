@@ -163,6 +163,7 @@ class DeviceBatch:
     segments: list = None                              # iteration ends of the launches of one run (None: one launch)
     cal: tuple = None                                  # (costs, ticks, tick_offset) for re-slicing between segments
     kernel_choice: dict = None                         # measured choice between the 4- and 3-CTAs-per-SM builds
+    progress: object = None                            # pinned int32 [R]: rows complete per chain, written by the kernel
 
 
 CALIBRATE_MIN_NITER = 2000     # shorter runs are not worth the calibration launches
@@ -271,7 +272,7 @@ class GibbsEngine:
 
     # ---- pack + upload -------------------------------------------------------------------
     def prepare(self, chains, ncomp, niter, thin=100, seed=0, flags=0, inject=None, n_waves=None, shard=None,
-                calibrate=None, segments=None, choose_kernel=None):
+                calibrate=None, segments=None, choose_kernel=None, progress_rows=0):
         """``chains``: list of :class:`ChainInput`.  ``inject``: dict with optional
         ``coef_c``/``coef_a`` (list of [niter,K] float32) and ``u`` (list of [niter,N]).
         ``shard`` (internal, see :func:`run_sharded`): this GPU's part of ONE chain split over
@@ -431,10 +432,17 @@ class GibbsEngine:
             b.trace_nk = dev_zeros('trace_nk', (R, niter, K), torch.int64)
             b.trace_tk = dev_zeros('trace_tk', (R, niter, K), torch.int64)
 
+        progress = None
+        if progress_rows and shard is None and K <= _cabi.LANE_MAX_NCOMP and \
+                not flags & (_cabi.FLAG_INJECT_COEF | _cabi.FLAG_INJECT_U | _cabi.FLAG_TRACE):
+            # mapped pinned host memory: with unified addressing the device writes through the same pointer
+            progress = torch.zeros(R, dtype=torch.int32).pin_memory()
+            b.progress, b.progress_rows = progress.data_ptr(), int(progress_rows)
         torch.cuda.current_stream(dev).synchronize()
         db = DeviceBatch(batch=b, plan=plan, tensors=T, host=H, order=order, n_data=n_data, ind_offset=ind_offset,
                          rows=rows, ncomp=K, niter=int(niter), flags=int(flags), h2d_bytes=h2d,
                          units=float(n_data.sum()) * K * int(niter))
+        db.progress = progress
         if wide:
             if calibrate:
                 raise ValueError(f'ncomp > {_cabi.LANE_MAX_NCOMP} has no schedule to calibrate')
@@ -492,6 +500,7 @@ class GibbsEngine:
         torch = self.torch
         cal = _cabi.Batch.from_buffer_copy(db.batch)
         cal.niter, cal.thin = int(iters), int(iters) + 2
+        cal.progress, cal.progress_rows = None, 0
         best = float('inf')
         with torch.cuda.device(self.device):
             s = torch.cuda.current_stream()
@@ -574,6 +583,7 @@ class GibbsEngine:
         cyc = torch.zeros(len(db.plan.tasks), dtype=torch.int64, device=T['tasks'].device)
         cal = _cabi.Batch.from_buffer_copy(db.batch)
         cal.niter, cal.thin = int(iters), int(iters) + 2            # no row is saved
+        cal.progress, cal.progress_rows = None, 0
         cal.task_cycles = cyc.data_ptr()
         self.reset(db)
         with torch.cuda.device(self.device):
@@ -655,6 +665,9 @@ class GibbsEngine:
         """Zero the exchange workspace and status so the same DeviceBatch can be launched again."""
         db.tensors['exchange'].zero_()
         db.tensors['status'].zero_()
+        if db.progress is not None:
+            self.torch.cuda.current_stream(db.tensors['status'].device).synchronize()
+            db.progress.zero_()
 
     def launch(self, db, stream=None):
         """Enqueue the whole run.  Long calibrated runs go as several back-to-back launches
@@ -911,11 +924,148 @@ class GibbsEngine:
             futures.append(pool.submit(on_chain, int(r), result(int(r))))
         return futures
 
+    def start_live_stream(self, db, on_chain, pool, dest=None, progress=None):
+        """Start bringing results home WHILE the sweep runs (call right before ``launch``; ``db`` must have been
+        prepared with ``progress_rows``).  Returns a :class:`LiveStream`; its ``finish()`` waits for the
+        launch, copies what is left and returns the futures of the ``on_chain`` calls."""
+        return LiveStream(self, db, on_chain, pool, dest=dest, progress=progress)
+
     def run(self, chains, ncomp, niter, thin=100, seed=0, flags=0, inject=None, n_waves=None):
         db = self.prepare(chains, ncomp, niter, thin=thin, seed=seed, flags=flags, inject=inject,
                           n_waves=n_waves)
         self.launch(db)
         return self.fetch(db)
+
+
+class LiveStream:
+    """Output path overlapped with the sweep.
+
+    The kernel publishes, per chain, how many saved rows are complete (``brta_batch.progress`` in mapped pinned
+    memory).  A poller thread turns newly finished row blocks -- contiguous byte ranges of the dense label
+    buffer -- into device-to-host copies on a copy stream, packed into the engine's ring of pinned staging
+    buffers; worker threads of ``pool`` scatter each staged buffer into the per-chain arrays and call
+    ``on_chain(r, ChainResult)`` (normally: write the pickle) when the last byte of chain r has landed.  When the
+    launch ends only the rows since the last publication are left to copy."""
+
+    POLL_SECONDS = 0.003
+    MIN_FLUSH_BYTES = 8 << 20
+
+    def __init__(self, engine, db, on_chain, pool, dest=None, progress=None):
+        import queue
+        import threading
+        if db.progress is None:
+            raise ValueError('the batch was prepared without progress_rows')
+        self.eng, self.db, self.on_chain, self.pool, self.report = engine, db, on_chain, pool, progress
+        torch = engine.torch
+        self.rows = db.rows
+        self.n = np.asarray(db.n_data, dtype=np.int64)
+        self.offs = np.asarray(db.ind_offset, dtype=np.int64)
+        self.dest = dest if dest is not None else [np.empty((self.rows, int(n)), dtype=np.uint8) for n in self.n]
+        self.done_rows = np.zeros(len(self.n), dtype=np.int64)
+        self.remaining = self.rows * self.n
+        self.lock = threading.Lock()
+        self.futures = []
+        self.ring = engine._ring()
+        self.free = queue.Queue()
+        for k in range(len(self.ring)):
+            self.free.put(k)
+        self.finished = []                                  # chains whose labels are all home (results need mcw / mcr)
+        self.stop = threading.Event()
+        self.error = None
+        with torch.cuda.device(engine.device):
+            self.launched = torch.cuda.Event()
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
+
+    # -- staging --------------------------------------------------------------------------
+    def _flush(self, slot, pieces, used):
+        torch = self.eng.torch
+        with torch.cuda.stream(self.eng._copy_stream):
+            ev = torch.cuda.Event()
+            ev.record()
+        self.futures.append(self.pool.submit(self._scatter, slot, pieces, ev))
+
+    def _scatter(self, slot, pieces, ev):
+        try:
+            ev.synchronize()
+            src = self.ring[slot].numpy()
+            done = []
+            for r, lo, pos, nbytes in pieces:
+                np.copyto(self.dest[r].reshape(-1)[lo:lo + nbytes], src[pos:pos + nbytes])
+                with self.lock:
+                    self.remaining[r] -= nbytes
+                    if self.remaining[r] == 0:
+                        done.append(r)
+        finally:
+            self.free.put(slot)
+        with self.lock:
+            self.finished.extend(done)
+
+    def _copy_rows(self, upto):
+        """Enqueue D2H of rows [done_rows[r], upto[r]) of every chain, packed into staging buffers."""
+        torch = self.eng.torch
+        flat = self.db.tensors['indicator']
+        chunk = self.eng.STREAM_CHUNK_BYTES
+        slot, pieces, used = None, [], 0
+        with torch.cuda.device(self.eng.device), torch.cuda.stream(self.eng._copy_stream):
+            for r in np.nonzero(upto > self.done_rows)[0]:
+                lo = int(self.done_rows[r] * self.n[r])
+                hi = int(upto[r] * self.n[r])
+                while lo < hi:
+                    if slot is None:
+                        slot, pieces, used = self.free.get(), [], 0
+                    take = min(hi - lo, chunk - used)
+                    a = int(self.offs[r]) + lo
+                    self.ring[slot][used:used + take].copy_(flat[a:a + take], non_blocking=True)
+                    pieces.append((int(r), lo, used, take))
+                    used += take
+                    lo += take
+                    if used == chunk:
+                        self._flush(slot, pieces, used)
+                        slot = None
+                self.done_rows[r] = upto[r]
+            if slot is not None:
+                self._flush(slot, pieces, used)
+
+    def _poll(self):
+        import time
+        try:
+            prog = self.db.progress.numpy()
+            while not self.stop.is_set():
+                now = np.minimum(prog.astype(np.int64), self.rows)          # snapshot of the device's words
+                ready = int(((now - self.done_rows) * self.n).sum())
+                if ready >= self.MIN_FLUSH_BYTES:
+                    self._copy_rows(now)
+                    if self.report is not None:
+                        self.report(int(now.min()) * (self.db.niter // max(self.rows, 1)), self.db.niter)
+                time.sleep(self.POLL_SECONDS)
+        except BaseException as e:                                          # surfaced by finish()
+            self.error = e
+
+    # -- end of the launch -------------------------------------------------------------------
+    def finish(self):
+        """Wait for the sweep, bring the rest home, hand every chain to ``on_chain``.  Returns the futures."""
+        torch = self.eng.torch
+        T = self.db.tensors
+        with torch.cuda.device(self.eng.device):
+            torch.cuda.current_stream().synchronize()                       # the sampler is done
+        self.stop.set()
+        self.thread.join()
+        if self.error is not None:
+            raise self.error
+        with torch.cuda.device(self.eng.device):
+            status = T['status'].cpu().numpy()
+            mcw = T['mcweights'].cpu().numpy()
+            mcr = T['mcrates'].cpu().numpy()
+        self._copy_rows(np.full(len(self.n), self.rows, dtype=np.int64))
+        for fut in list(self.futures):
+            fut.result()                                                    # all labels are home
+        rows = self.rows
+
+        def deliver(r):
+            self.on_chain(r, ChainResult(mcweights=mcw[r, :rows].copy(), mcrates=mcr[r, :rows].copy(),
+                                         indicator=self.dest[r], status=int(status[r])))
+        return [self.pool.submit(deliver, r) for r in range(len(self.n))]
 
 
 def shard_bounds(n_data, n_shards):

@@ -258,6 +258,84 @@ class _RefUnpickler(pickle.Unpickler):
         return super().find_class(module, name)
 
 
+class _DeferredPickler(_RefPickler):
+    """The reference pickle with HOLES: the payload of selected arrays is not written; the stream records where it
+    belongs (``offsets[name]`` = byte position in the file) and skips that many bytes.  Everything else -- opcodes,
+    memo indices, the length prefix of the skipped payload -- is the stream ``_RefPickler`` writes (up to the
+    placement of FRAME marks, which unpicklers skip), so filling the holes later yields the pickle of the
+    finished object."""
+    dispatch = _RefPickler.dispatch.copy()
+
+    def __init__(self, file, deferred):
+        super().__init__(file)
+        self._out = file
+        self._deferred = {int(a.__array_interface__['data'][0]): name for name, a in deferred.items()}
+        self.offsets = {}
+
+    def _save_buffer_deferred(self, obj):
+        with obj.raw() as m:
+            name = self._deferred.get(int(np.asarray(m).__array_interface__['data'][0])) if m.nbytes else None
+            if name is None:
+                return _RefPickler._save_buffer_in_band(self, obj)
+            header = (pickle.BINBYTES8 if m.readonly else pickle.BYTEARRAY8) + struct.pack('<Q', m.nbytes)
+            self.framer.commit_frame(force=True)               # everything so far is in the file
+            self._out.write(header)
+            self.offsets[name] = self._out.tell()
+            self._out.seek(m.nbytes, os.SEEK_CUR)              # the hole
+
+    dispatch[pickle.PickleBuffer] = _save_buffer_deferred
+
+
+class DeferredPickle:
+    """``gibbs_{niter}.pkl`` of a residue created BEFORE its chain has finished: the label array of the file is
+    a hole that the output path fills in place (``indicator`` is a memory map of that region, so bringing the
+    labels home IS writing the file), ``mcweights`` / ``mcrates`` are patched in at the end.  Same opcodes and
+    payloads as ``Gibbs.save`` of the finished object, same ``.bak`` rotation (gibbs.py:336-349)."""
+
+    def __init__(self, gb, rows):
+        self.gb = gb
+        savedir = gb._savedir() + '/'
+        self.path = savedir + f'gibbs_{gb.niter}.pkl'
+        if not os.path.exists(savedir):
+            raise OSError(f'No such directory: {savedir}')
+        self.rotated = os.path.exists(self.path)
+        if self.rotated:
+            os.rename(self.path, self.path + '.bak')
+        n = len(gb.times)
+        gb.indicator = np.empty((rows, n), dtype=np.uint8)     # never touched: stands for the hole
+        with open(self.path, 'w+b') as f:
+            pk = _DeferredPickler(f, {'indicator': gb.indicator, 'mcweights': gb.mcweights, 'mcrates': gb.mcrates})
+            pk.dump(gb)
+        self.offsets = pk.offsets
+        if rows * n:
+            # a plain ndarray over the mapping (its base keeps the map alive): pickles, copies and compares like any array
+            self.indicator = np.memmap(self.path, dtype=np.uint8, mode='r+', offset=self.offsets['indicator'],
+                                       shape=(rows, n)).view(np.ndarray)
+        else:
+            self.indicator = np.empty((rows, n), dtype=np.uint8)
+        gb.indicator = None
+
+    def complete(self, mcweights, mcrates):
+        gb = self.gb
+        gb.mcweights, gb.mcrates, gb.indicator = mcweights, mcrates, self.indicator
+        with open(self.path, 'r+b') as f:
+            for name in ('mcweights', 'mcrates'):
+                arr = np.ascontiguousarray(getattr(gb, name), dtype=np.float64)
+                if arr.nbytes:
+                    f.seek(self.offsets[name])
+                    f.write(arr.data)
+
+    def abandon(self):
+        """The chain failed: no new file, and the previous one back in place."""
+        self.indicator = None
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if self.rotated and os.path.exists(self.path + '.bak'):
+            os.rename(self.path + '.bak', self.path)
+
+
 def dump_reference_pickle(obj, f):
     _RefPickler(f).dump(obj)
 
@@ -286,10 +364,12 @@ def _pick_device(device, loc=0):
 
 
 WRITER_THREADS = 8
+PROGRESS_ROWS = 16             # the kernel publishes finished rows in blocks of this many
+LIVE_MIN_BYTES = 64 << 20      # smaller label volumes are not worth a poller thread
 
 
 def run_batch(gibbs_list, device=None, seed=None, prepared=False, engine=None, save=False,
-              keep_indicator_on_device=False, pool=None, progress=None):
+              keep_indicator_on_device=False, pool=None, progress=None, live=True):
     """Run many residues' chains in ONE launch on one GPU and fill their output arrays.
 
     All members must share ``ncomp``, ``niter`` and ``g`` (``ParallelGibbs`` guarantees it,
@@ -300,6 +380,11 @@ def run_batch(gibbs_list, device=None, seed=None, prepared=False, engine=None, s
     ends with a non-zero device status is not assigned; all others are assigned (and, with ``save``,
     pickled by a pool of writer threads while the rest of the labels are still coming back over PCIe).
     Failures are reported together at the end as :class:`GibbsBatchError`.
+
+    ``live`` (default): large batches come home WHILE the sweep runs -- the kernel publishes finished row
+    blocks, a poller copies them out (``engine.LiveStream``) and, with ``save``, straight into the label region
+    of each residue's pickle (:class:`DeferredPickle`; ``indicator`` is then a memory map of the file).
+    ``progress(done_iterations, niter)`` is called as the slowest chain of the batch advances.
     """
     if not gibbs_list:
         return
@@ -323,10 +408,14 @@ def run_batch(gibbs_list, device=None, seed=None, prepared=False, engine=None, s
             seed = getattr(first, 'seed', None)
         if seed is None:
             seed = _fresh_seed()
+        rows = (first.niter + 1) // first.g
+        label_bytes = rows * sum(len(gb.times) for gb in members)
+        want_live = bool(live) and not keep_indicator_on_device and rows >= 4 * PROGRESS_ROWS and label_bytes >= LIVE_MIN_BYTES
         nvtx = eng.torch.cuda.nvtx                             # ranges for nsys / ncu timelines
         nvtx.range_push(f'brta prepare {len(members)} residues')
         try:
-            db = eng.prepare(inputs, first.ncomp, first.niter, thin=first.g, seed=seed)
+            db = eng.prepare(inputs, first.ncomp, first.niter, thin=first.g, seed=seed,
+                             progress_rows=PROGRESS_ROWS if want_live else 0)
         finally:
             nvtx.range_pop()
         if progress is not None:
@@ -335,6 +424,13 @@ def run_batch(gibbs_list, device=None, seed=None, prepared=False, engine=None, s
         eng.launch(db)
         nvtx.range_pop()
         lock = threading.Lock()
+        if db.progress is not None:
+            _finish_live(eng, db, members, save, pool, progress, failures, lock)
+            if progress is not None:
+                progress(first.niter, first.niter)
+            if failures:
+                raise GibbsBatchError(failures)
+            return
 
         def on_chain(r, res):
             gb = members[r]
@@ -368,6 +464,51 @@ def run_batch(gibbs_list, device=None, seed=None, prepared=False, engine=None, s
             progress(first.niter, first.niter)
     if failures:
         raise GibbsBatchError(failures)
+
+
+def _finish_live(eng, db, members, save, pool, progress, failures, lock):
+    """The overlapped output path of :func:`run_batch`: labels stream into their final place while the launch
+    runs; after it, only the last row block, the (tiny) weights / rates and the bookkeeping are left."""
+    deferred = [None] * len(members)
+    dest = None
+    if save:
+        dest = []
+        for r, gb in enumerate(members):
+            try:
+                os.makedirs(gb._savedir(), exist_ok=True)
+                deferred[r] = DeferredPickle(gb, db.rows)
+                dest.append(deferred[r].indicator)
+            except Exception as e:                          # e.g. disk full: this residue only (labels go to memory)
+                failures.append((gb.residue, e))
+                dest.append(np.empty((db.rows, len(gb.times)), dtype=np.uint8))
+
+    def on_chain(r, res):
+        gb = members[r]
+        err = _status_error(gb.residue, res.status)
+        try:
+            if err is None and (not save or deferred[r] is not None):
+                if save:
+                    deferred[r].complete(res.mcweights, res.mcrates)
+                else:
+                    gb.mcweights, gb.mcrates, gb.indicator = res.mcweights, res.mcrates, res.indicator
+                gb.__dict__.pop('_device_indicator', None)
+            elif deferred[r] is not None:
+                deferred[r].abandon()
+        except Exception as e:
+            err = e
+        if err is not None:
+            with lock:
+                failures.append((gb.residue, err))
+
+    own_pool = pool is None
+    pool = ThreadPoolExecutor(max_workers=WRITER_THREADS) if own_pool else pool
+    try:
+        stream = eng.start_live_stream(db, on_chain, pool, dest=dest, progress=progress)
+        for fut in stream.finish():
+            fut.result()
+    finally:
+        if own_pool:
+            pool.shutdown(wait=True)
 
 
 class ParallelGibbs(object):

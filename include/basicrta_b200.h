@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BRTA_ABI_VERSION 4
+#define BRTA_ABI_VERSION 5
 
 /* compile-time geometry of the sampler kernel */
 #ifndef BRTA_THREADS
@@ -212,7 +212,15 @@ typedef struct brta_batch {
     uint64_t         watchdog_ns;
     int32_t          device;       /* CUDA ordinal the pointers live on; the call runs there and restores
                                       the caller's current device.  -1 = the current device */
-    int32_t          reserved0;
+    /* live progress (optional; ncomp <= 32, not sharded): every `progress_rows` saved rows the kernel
+     * stores, per chain, the number of rows that are COMPLETE -- labels of every team member, weights and
+     * rates written and visible system-wide (fence.sys on both sides of the team exchange) -- into
+     * progress[r].  With `progress` in mapped pinned host memory the caller can copy finished row blocks
+     * out (cudaMemcpyAsync on another stream) and write them to disk while the sweep is still running,
+     * and drive a progress bar (the reference has one tqdm bar per chain, gibbs.py:191-193).  The rows after
+     * the last multiple of progress_rows are complete when the launch is. */
+    int32_t          progress_rows; /* 0 = off */
+    int32_t*         progress;      /* [R], may be NULL */
 } brta_batch;
 
 /* Device capabilities.  Python side: Gibbs.run needs it to size the schedule. */

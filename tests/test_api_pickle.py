@@ -102,6 +102,57 @@ def test_pickle_stream_names_the_reference_classes(tmp_path, monkeypatch):
     assert obj.niter == 3000 and obj.residue == 'W313'
 
 
+def test_deferred_pickle_equals_a_saved_object(tmp_path, monkeypatch):
+    """The overlapped output path creates ``gibbs_{niter}.pkl`` before the chain has finished: the label array is
+    a hole of the file that is filled in place (``indicator`` = a memory map of it), weights and rates are
+    patched in at the end (gibbs.DeferredPickle).  The result must unpickle to exactly what ``save`` of the
+    finished object gives -- also through the plain ``pickle.load`` a stock basicrta uses --, rotate ``.bak``
+    like gibbs.py:343-344, and vanish (previous file restored) if the chain fails."""
+    import io
+    import pickletools
+    from basicrta_b200.gibbs import DeferredPickle, dump_reference_pickle
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.default_rng(3)
+    for n, niter, thin in ((4000, 3000, 10), (7, 300, 100), (3, 50, 100)):
+        rows = (niter + 1) // thin
+        times = np.ceil(rng.exponential(1.0, n) / 0.1) * 0.1
+        gb = Gibbs(times, 'D1', 0, ncomp=5, niter=niter, cutoff=7.0)
+        gb.g = thin
+        gb._prepare(allocate_indicator=False)
+        os.makedirs(gb._savedir(), exist_ok=True)
+        dp = DeferredPickle(gb, rows)
+        assert gb.indicator is None and dp.indicator.shape == (rows, n)
+        ind = rng.integers(0, 5, size=(rows, n)).astype(np.uint8)
+        w, r = rng.random((rows, 5)), rng.random((rows, 5))
+        dp.indicator[...] = ind                               # what the staging threads do, block by block
+        dp.complete(w, r)
+        assert gb.indicator is dp.indicator and np.array_equal(gb.mcweights, w)
+        raw = open(dp.path, 'rb').read()
+        ops = [(op.name, a) for op, a, _ in pickletools.genops(io.BytesIO(raw))]
+        assert ('SHORT_BINUNICODE', 'basicrta.gibbs') in ops and not any('basicrta_b200' in str(a) for _, a in ops)
+        back = Gibbs.load(dp.path)
+        ref = io.BytesIO()
+        dump_reference_pickle(gb, ref)
+        plain = Gibbs.load.__func__ if hasattr(Gibbs.load, '__func__') else Gibbs.load
+        for name in ('indicator', 'mcweights', 'mcrates', 'times', 't', 's', 'whypers', 'rhypers'):
+            assert np.array_equal(getattr(back, name), {'indicator': ind, 'mcweights': w, 'mcrates': r}.get(name, getattr(gb, name)))
+        assert back.niter == niter and back.g == thin and back.residue == 'D1'
+        # same object graph as a plain save of the finished object (framing aside)
+        def ops_of(b):
+            return [(op.name, a if not isinstance(a, (bytes, bytearray)) else len(a))
+                    for op, a, _ in pickletools.genops(io.BytesIO(b)) if op.name != 'FRAME']
+        assert ops_of(raw) == ops_of(ref.getvalue())
+        # .bak rotation and failure handling
+        gb2 = Gibbs(times, 'D1', 0, ncomp=5, niter=niter, cutoff=7.0)
+        gb2.g = thin
+        gb2._prepare(allocate_indicator=False)
+        dp2 = DeferredPickle(gb2, rows)
+        assert os.path.exists(dp.path + '.bak')
+        dp2.abandon()
+        assert not os.path.exists(dp.path + '.bak') and open(dp.path, 'rb').read() == raw
+        os.remove(dp.path)
+
+
 def test_results_stand_in_behaves_like_the_mdanalysis_class():
     from basicrta_b200.results import Results
     r = Results()

@@ -308,3 +308,39 @@ def test_many_chains_per_launch(engine):
         solo = engine.run([chains[r]], K, niter, thin=thin, seed=3)[0]
         assert np.array_equal(solo.indicator, res[r].indicator)
         assert np.array_equal(solo.mcweights, res[r].mcweights) and np.array_equal(solo.mcrates, res[r].mcrates)
+
+
+def test_live_stream_brings_rows_home_during_the_run(engine):
+    """Output path overlapped with the sweep: the kernel publishes per chain how many saved
+    rows are complete (brta_batch.progress, mapped pinned memory); a poller copies finished row blocks out
+    while the launch is still running.  The result must equal the plain fetch, for multi-CTA teams, ragged
+    sizes and a row count that is not a multiple of the publication interval."""
+    from concurrent.futures import ThreadPoolExecutor
+    rng = np.random.default_rng(17)
+    chains = []
+    for r, n in enumerate((52000, 9001, 700, 33, 18000)):
+        comp = rng.choice(3, size=n, p=[0.8, 0.15, 0.05])
+        x = rng.exponential(1.0 / np.array([4.0, 0.1, 0.002])[comp])
+        chains.append(ChainInput(ticks=np.maximum(np.ceil(x / 0.1), 1).astype(np.int64), ts=0.1, chain_id=60 + r))
+    K, niter, thin = 15, 3050, 10                                           # 305 rows, published every 16
+    ref = engine.run(chains, K, niter, thin=thin, seed=4)
+    db = engine.prepare(chains, K, niter, thin=thin, seed=4, progress_rows=16)
+    assert db.progress is not None
+    got = {}
+    reports = []
+    with ThreadPoolExecutor(max_workers=4) as pool:
+        live = engine.start_live_stream(db, lambda r, res: got.__setitem__(r, res), pool,
+                                        progress=lambda done, total: reports.append((done, total)))
+        live.MIN_FLUSH_BYTES = 1 << 16                                      # small batch: stream anyway
+        engine.launch(db)
+        for fut in live.finish():
+            fut.result()
+    assert sorted(got) == list(range(len(chains)))
+    assert int(db.progress.numpy().min()) == 304                            # 19 publications of 16 rows
+    for r, a in enumerate(ref):
+        b = got[r]
+        assert a.status == 0 and b.status == 0
+        np.testing.assert_array_equal(a.mcweights, b.mcweights)
+        np.testing.assert_array_equal(a.mcrates, b.mcrates)
+        np.testing.assert_array_equal(a.indicator, b.indicator)
+    assert reports and all(t == niter for _, t in reports)
