@@ -21,6 +21,7 @@ exchange           BRTA_EXCH_BYTES(team)/chain tagged mailboxes of integer team 
 =================  ==========================  ==========================================
 """
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -831,6 +832,9 @@ class GibbsEngine:
 
     def _ring(self):
         """Pinned staging buffers, allocated once per engine (page-locking memory is slow: ~0.3 s/GB)."""
+        if getattr(self, '_ring_lock', None) is None:
+            import threading
+            self._ring_lock = threading.Lock()
         if getattr(self, '_ring_bufs', None) is None:
             torch = self.torch
             self._ring_bufs = [torch.empty(self.STREAM_CHUNK_BYTES, dtype=torch.uint8, pin_memory=True)
@@ -879,6 +883,7 @@ class GibbsEngine:
             return [pool.submit(on_chain, r, result(r)) for r in range(R)]
 
         ring = self._ring()
+        self._ring_lock.acquire()                                           # released when the last chunk has been scattered
         free = queue.Queue()                                                # indices of staging buffers not in use
         for k in range(len(ring)):
             free.put(k)
@@ -911,24 +916,37 @@ class GibbsEngine:
             for r in done:
                 on_chain(r, result(r))
 
-        with torch.cuda.device(self.device):
-            for a in range(0, total, self.STREAM_CHUNK_BYTES):
-                b = min(a + self.STREAM_CHUNK_BYTES, total)
-                slot = free.get()
-                with torch.cuda.stream(self._copy_stream):
-                    ring[slot][:b - a].copy_(flat[a:b], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record()
-                futures.append(pool.submit(scatter, slot, a, b, ev))
+        try:
+            with torch.cuda.device(self.device):
+                for a in range(0, total, self.STREAM_CHUNK_BYTES):
+                    b = min(a + self.STREAM_CHUNK_BYTES, total)
+                    slot = free.get()
+                    with torch.cuda.stream(self._copy_stream):
+                        ring[slot][:b - a].copy_(flat[a:b], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record()
+                    futures.append(pool.submit(scatter, slot, a, b, ev))
+        except BaseException:
+            self._ring_lock.release()
+            raise
         for r in np.nonzero(sizes == 0)[0]:
             futures.append(pool.submit(on_chain, int(r), result(int(r))))
+        chunk_futures = list(futures)
+
+        def release():
+            for f in chunk_futures:
+                f.exception()                                               # wait; errors surface through the caller's result()
+            self._ring_lock.release()
+        threading.Thread(target=release, daemon=True).start()
         return futures
 
-    def start_live_stream(self, db, on_chain, pool, dest=None, progress=None):
+    def start_live_stream(self, db, on_chain, pool, dest=None, progress=None, sinks=None):
         """Start bringing results home WHILE the sweep runs (call right before ``launch``; ``db`` must have been
         prepared with ``progress_rows``).  Returns a :class:`LiveStream`; its ``finish()`` waits for the
-        launch, copies what is left and returns the futures of the ``on_chain`` calls."""
-        return LiveStream(self, db, on_chain, pool, dest=dest, progress=progress)
+        launch, copies what is left and returns the futures of the ``on_chain`` calls.  ``sinks[r]`` = ``(fd, offset)``
+        sends chain r's labels straight into a file (``os.pwrite`` from the staging buffer: 2-3 times the
+        throughput of stores into a memory map of the same pages) instead of into ``dest[r]``."""
+        return LiveStream(self, db, on_chain, pool, dest=dest, progress=progress, sinks=sinks)
 
     def run(self, chains, ncomp, niter, thin=100, seed=0, flags=0, inject=None, n_waves=None):
         db = self.prepare(chains, ncomp, niter, thin=thin, seed=seed, flags=flags, inject=inject,
@@ -950,7 +968,7 @@ class LiveStream:
     POLL_SECONDS = 0.003
     MIN_FLUSH_BYTES = 8 << 20
 
-    def __init__(self, engine, db, on_chain, pool, dest=None, progress=None):
+    def __init__(self, engine, db, on_chain, pool, dest=None, progress=None, sinks=None):
         import queue
         import threading
         if db.progress is None:
@@ -960,12 +978,17 @@ class LiveStream:
         self.rows = db.rows
         self.n = np.asarray(db.n_data, dtype=np.int64)
         self.offs = np.asarray(db.ind_offset, dtype=np.int64)
-        self.dest = dest if dest is not None else [np.empty((self.rows, int(n)), dtype=np.uint8) for n in self.n]
+        self.sinks = sinks if sinks is not None else [None] * len(self.n)
+        self.dest = list(dest) if dest is not None else [None] * len(self.n)
+        for r, n in enumerate(self.n):
+            if self.dest[r] is None and self.sinks[r] is None:
+                self.dest[r] = np.empty((self.rows, int(n)), dtype=np.uint8)
         self.done_rows = np.zeros(len(self.n), dtype=np.int64)
         self.remaining = self.rows * self.n
         self.lock = threading.Lock()
         self.futures = []
         self.ring = engine._ring()
+        engine._ring_lock.acquire()                         # one batch at a time uses the engine's staging ring
         self.free = queue.Queue()
         for k in range(len(self.ring)):
             self.free.put(k)
@@ -991,7 +1014,14 @@ class LiveStream:
             src = self.ring[slot].numpy()
             done = []
             for r, lo, pos, nbytes in pieces:
-                np.copyto(self.dest[r].reshape(-1)[lo:lo + nbytes], src[pos:pos + nbytes])
+                if self.sinks[r] is not None:
+                    fd, base = self.sinks[r]
+                    view, at = memoryview(src[pos:pos + nbytes]), base + lo
+                    while len(view):                                 # pwrite may write less than asked
+                        k = os.pwrite(fd, view, at)
+                        view, at = view[k:], at + k
+                else:
+                    np.copyto(self.dest[r].reshape(-1)[lo:lo + nbytes], src[pos:pos + nbytes])
                 with self.lock:
                     self.remaining[r] -= nbytes
                     if self.remaining[r] == 0:
@@ -1052,14 +1082,18 @@ class LiveStream:
         self.stop.set()
         self.thread.join()
         if self.error is not None:
+            self.eng._ring_lock.release()
             raise self.error
         with torch.cuda.device(self.eng.device):
             status = T['status'].cpu().numpy()
             mcw = T['mcweights'].cpu().numpy()
             mcr = T['mcrates'].cpu().numpy()
-        self._copy_rows(np.full(len(self.n), self.rows, dtype=np.int64))
-        for fut in list(self.futures):
-            fut.result()                                                    # all labels are home
+        try:
+            self._copy_rows(np.full(len(self.n), self.rows, dtype=np.int64))
+            for fut in list(self.futures):
+                fut.result()                                                # all labels are home
+        finally:
+            self.eng._ring_lock.release()
         rows = self.rows
 
         def deliver(r):

@@ -307,27 +307,46 @@ class DeferredPickle:
             pk = _DeferredPickler(f, {'indicator': gb.indicator, 'mcweights': gb.mcweights, 'mcrates': gb.mcrates})
             pk.dump(gb)
         self.offsets = pk.offsets
-        if rows * n:
-            # a plain ndarray over the mapping (its base keeps the map alive): pickles, copies and compares like any array
-            self.indicator = np.memmap(self.path, dtype=np.uint8, mode='r+', offset=self.offsets['indicator'],
-                                       shape=(rows, n)).view(np.ndarray)
-        else:
-            self.indicator = np.empty((rows, n), dtype=np.uint8)
+        self.shape = (rows, n)
+        self._map = None
+        self.fd = os.open(self.path, os.O_RDWR)                # the staging threads pwrite the label blocks through it
         gb.indicator = None
+
+    @property
+    def sink(self):
+        """(fd, offset) of the label region, or None if there is none (no rows)."""
+        return (self.fd, self.offsets['indicator']) if self.shape[0] * self.shape[1] else None
+
+    @property
+    def indicator(self):
+        """The label region of the file as an array: a plain ndarray over a memory map (its base keeps the map
+        alive), so it pickles, copies and compares like any array."""
+        if self._map is None:
+            if self.shape[0] * self.shape[1]:
+                self._map = np.memmap(self.path, dtype=np.uint8, mode='r+', offset=self.offsets['indicator'],
+                                      shape=self.shape).view(np.ndarray)
+            else:
+                self._map = np.empty(self.shape, dtype=np.uint8)
+        return self._map
+
+    def _close(self):
+        if self.fd is not None:
+            os.close(self.fd)
+            self.fd = None
 
     def complete(self, mcweights, mcrates):
         gb = self.gb
+        for name, value in (('mcweights', mcweights), ('mcrates', mcrates)):
+            arr = np.ascontiguousarray(value, dtype=np.float64)
+            if arr.nbytes:
+                os.pwrite(self.fd, arr.data, self.offsets[name])
+        self._close()
         gb.mcweights, gb.mcrates, gb.indicator = mcweights, mcrates, self.indicator
-        with open(self.path, 'r+b') as f:
-            for name in ('mcweights', 'mcrates'):
-                arr = np.ascontiguousarray(getattr(gb, name), dtype=np.float64)
-                if arr.nbytes:
-                    f.seek(self.offsets[name])
-                    f.write(arr.data)
 
     def abandon(self):
         """The chain failed: no new file, and the previous one back in place."""
-        self.indicator = None
+        self._close()
+        self._map = None
         try:
             os.remove(self.path)
         except OSError:
@@ -364,7 +383,7 @@ def _pick_device(device, loc=0):
 
 
 WRITER_THREADS = 8
-PROGRESS_ROWS = 16             # the kernel publishes finished rows in blocks of this many
+PROGRESS_ROWS = 32             # the kernel publishes finished rows in blocks of this many
 LIVE_MIN_BYTES = 64 << 20      # smaller label volumes are not worth a poller thread
 
 
@@ -470,17 +489,16 @@ def _finish_live(eng, db, members, save, pool, progress, failures, lock):
     """The overlapped output path of :func:`run_batch`: labels stream into their final place while the launch
     runs; after it, only the last row block, the (tiny) weights / rates and the bookkeeping are left."""
     deferred = [None] * len(members)
-    dest = None
+    sinks = None
     if save:
-        dest = []
+        sinks = [None] * len(members)
         for r, gb in enumerate(members):
             try:
                 os.makedirs(gb._savedir(), exist_ok=True)
                 deferred[r] = DeferredPickle(gb, db.rows)
-                dest.append(deferred[r].indicator)
+                sinks[r] = deferred[r].sink
             except Exception as e:                          # e.g. disk full: this residue only (labels go to memory)
                 failures.append((gb.residue, e))
-                dest.append(np.empty((db.rows, len(gb.times)), dtype=np.uint8))
 
     def on_chain(r, res):
         gb = members[r]
@@ -503,7 +521,7 @@ def _finish_live(eng, db, members, save, pool, progress, failures, lock):
     own_pool = pool is None
     pool = ThreadPoolExecutor(max_workers=WRITER_THREADS) if own_pool else pool
     try:
-        stream = eng.start_live_stream(db, on_chain, pool, dest=dest, progress=progress)
+        stream = eng.start_live_stream(db, on_chain, pool, progress=progress, sinks=sinks)
         for fut in stream.finish():
             fut.result()
     finally:

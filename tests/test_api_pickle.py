@@ -121,10 +121,14 @@ def test_deferred_pickle_equals_a_saved_object(tmp_path, monkeypatch):
         gb._prepare(allocate_indicator=False)
         os.makedirs(gb._savedir(), exist_ok=True)
         dp = DeferredPickle(gb, rows)
-        assert gb.indicator is None and dp.indicator.shape == (rows, n)
+        assert gb.indicator is None and dp.shape == (rows, n) and (dp.sink is None) == (rows * n == 0)
         ind = rng.integers(0, 5, size=(rows, n)).astype(np.uint8)
         w, r = rng.random((rows, 5)), rng.random((rows, 5))
-        dp.indicator[...] = ind                               # what the staging threads do, block by block
+        if dp.sink is not None:                               # what the staging threads do, block by block
+            fd, base = dp.sink
+            flat = ind.reshape(-1)
+            for a in range(0, flat.size, 4096):
+                os.pwrite(fd, flat[a:a + 4096].data, base + a)
         dp.complete(w, r)
         assert gb.indicator is dp.indicator and np.array_equal(gb.mcweights, w)
         raw = open(dp.path, 'rb').read()
