@@ -119,3 +119,36 @@ def test_times_that_are_not_on_the_reference_ts_grid(tmp_path, monkeypatch):
     assert abs(sparse.ts - 0.4) < 1e-12
     sparse.run()
     assert sparse.indicator.shape == (3, 7) and np.all(np.isfinite(sparse.mcrates))
+
+
+def test_overlapped_output_path_equals_the_plain_one(tmp_path, monkeypatch):
+    """A batch large enough for the live path (>= 64 MB of labels): rows are copied out while the sweep runs and
+    written into holes of the pickle files (engine.LiveStream, gibbs.DeferredPickle).  Same seed, same residue
+    names => the arrays in memory, and what Gibbs.load reads back from disk, must equal the plain path's
+    (labels fetched after the launch, pickle.dump)."""
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.default_rng(12)
+    times = []
+    for n in (90000, 61000, 30000, 45000, 12000, 70001):
+        comp = rng.choice(3, size=n, p=[0.8, 0.15, 0.05])
+        times.append(np.ceil(rng.exponential(1.0 / np.array([4.0, 0.1, 0.002])[comp]) / 0.1) * 0.1)
+
+    def make(cutoff):
+        gl = [Gibbs(t, f'L{i}', 0, ncomp=15, niter=3000, cutoff=cutoff) for i, t in enumerate(times)]
+        for g in gl:
+            g.g = 10                                           # 300 saved rows -> 92 MB of labels
+        return gl
+    plain, live = make(1.0), make(1.0)
+    run_batch(plain, device=0, seed=5, save=False, live=False)
+    seen = []
+    run_batch(live, device=0, seed=5, save=True, progress=lambda done, total: seen.append(done))
+    assert seen[0] == 0 and seen[-1] == 3000 and seen == sorted(seen) and len(seen) > 2
+    for a, b in zip(plain, live):
+        np.testing.assert_array_equal(a.mcweights, b.mcweights)
+        np.testing.assert_array_equal(a.mcrates, b.mcrates)
+        np.testing.assert_array_equal(a.indicator, b.indicator)
+        back = Gibbs.load(f'basicrta-1.0/{b.residue}/gibbs_3000.pkl')
+        np.testing.assert_array_equal(back.indicator, a.indicator)
+        np.testing.assert_array_equal(back.mcrates, a.mcrates)
+        np.testing.assert_array_equal(back.times, a.times)
+        assert back.g == 10 and back.indicator.dtype == np.uint8
