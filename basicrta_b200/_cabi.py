@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, 'csrc')
 OBJ_DIR = os.path.join(CSRC, '_obj')
 INCLUDE = os.path.join(os.path.dirname(HERE), 'include')
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 THREADS = 128
 MAX_NCOMP = 255
 LANE_MAX_NCOMP = 32
@@ -38,6 +38,10 @@ FLAG_INJECT_U = 4
 FLAG_TRACE = 8
 FLAG_NO_TABLE = 16
 FLAG_CTAS3 = 32
+
+GMM_MAX_COMPONENTS = 16
+GMM_MAX_POINTS = 26624
+GMM_CONVERGED, GMM_NOT_CONVERGED, GMM_ILL_DEFINED = 0, 1, 2
 
 STATUS_OK = 0
 STATUS_NONFINITE = 1
@@ -87,10 +91,20 @@ class Batch(C.Structure):
     ]
 
 
+class GmmBatch(C.Structure):
+    _fields_ = [('n_problems', C.c_int32), ('n_init', C.c_int32), ('max_iter', C.c_int32), ('kmeans_max_iter', C.c_int32),
+                ('max_points', C.c_int32), ('class_mask', C.c_int32),
+                ('tol', C.c_double), ('reg_covar', C.c_double), ('kmeans_tol', C.c_double), ('seed', C.c_uint64),
+                ('x', C.c_void_p), ('offsets', C.c_void_p), ('n_components', C.c_void_p), ('problem_id', C.c_void_p),
+                ('init_params', C.c_void_p), ('lower_bound', C.c_void_p), ('n_iter', C.c_void_p), ('status', C.c_void_p),
+                ('params', C.c_void_p), ('init_out', C.c_void_p)]
+
+
 EXPORTS = ('brta_abi_version', 'brta_last_error', 'brta_query', 'brta_gibbs_launch_info',
            'brta_gibbs_run_batch', 'brta_philox_fill', 'brta_mufu_probe', 'brta_enable_peer_access',
            'brta_pindicator_counts', 'brta_gamma_fill', 'brta_shard_mailbox_create', 'brta_shard_mailbox_open',
-           'brta_shard_mailbox_close', 'brta_shard_mailbox_destroy', 'brta_shard_mailbox_clear')
+           'brta_shard_mailbox_close', 'brta_shard_mailbox_destroy', 'brta_shard_mailbox_clear',
+           'brta_gmm_fit_batch', 'brta_gmm_predict')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '-Xcompiler', '-fPIC']
@@ -112,7 +126,8 @@ def build(force=False, verbose=False, extra_flags=(), lib_path=None, ncomps=SWEE
     tag = ('_' + str(abs(hash(tuple(extra_flags))) % 10 ** 8)) if extra_flags else ''
     units = [('host' + tag, os.path.join(CSRC, 'brta_gibbs.cu'), []),
              ('pindicator' + tag, os.path.join(CSRC, 'brta_pindicator.cu'), []),
-             ('wide' + tag, os.path.join(CSRC, 'brta_wide.cu'), [])]
+             ('wide' + tag, os.path.join(CSRC, 'brta_wide.cu'), []),
+             ('gmm' + tag, os.path.join(CSRC, 'brta_gmm.cu'), ['-fmad=false'])]
     units += [(f'sweep_k{k}' + tag, os.path.join(CSRC, 'brta_sweep_inst.cu'), [f'-DBRTA_INST_K={k}']) for k in ncomps]
     objs = [os.path.join(OBJ_DIR, name + '.o') for name, _, _ in units]
     if not force and _newer(lib_path, HEADERS + [u[1] for u in units]):
@@ -167,6 +182,9 @@ def load():
                                            C.c_int32, C.c_void_p, C.c_void_p]
     lib.brta_gamma_fill.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint64,
                                     C.c_void_p]
+    lib.brta_gmm_fit_batch.argtypes = [C.POINTER(GmmBatch), C.c_void_p]
+    lib.brta_gmm_predict.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]
     lib.brta_shard_mailbox_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_char_p]
     lib.brta_shard_mailbox_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
     lib.brta_shard_mailbox_close.argtypes = [C.c_int, C.c_void_p]

@@ -197,13 +197,15 @@ class Gibbs(object):
         return g
 
     # ---- posterior processing: host side, see postprocess.py -------------------------------
-    def cluster(self, method='GaussianMixture', device=None, **kwargs):
+    def cluster(self, method='GaussianMixture', device=None, gmm_device=None, **kwargs):
+        """gibbs.py:221-273.  ``device``: GPU for the membership counts; ``gmm_device``: GPU for the mixture fit
+        (``basicrta_b200.gmm``) instead of scikit-learn."""
         from . import postprocess
-        return postprocess.cluster(self, method=method, device=device, **kwargs)
+        return postprocess.cluster(self, method=method, device=device, gmm_device=gmm_device, **kwargs)
 
-    def process_gibbs(self, save=True, device=None):
+    def process_gibbs(self, save=True, device=None, gmm_device=None):
         from . import postprocess
-        return postprocess.process_gibbs(self, save=save, device=device)
+        return postprocess.process_gibbs(self, save=save, device=device, gmm_device=gmm_device)
 
     def estimate_tau(self):
         from . import postprocess

@@ -29,12 +29,10 @@ def _mode(values):
     return stats.mode(values).mode
 
 
-def cluster(gibbs, method='GaussianMixture', device=None, **kwargs):
-    """Cluster the retained (weight, rate) samples in log space and accumulate, per datum,
-    how often its label fell in each cluster (gibbs.py:221-273).  ``device``: GPU index to run the
-    accumulation on (``engine.pindicator_counts``, same integers); None keeps it in NumPy."""
-    from sklearn import mixture
-
+def cluster_inputs(gibbs):
+    """What ``Gibbs.cluster`` feeds the mixture model (gibbs.py:230-252): the training points (rows with the
+    modal number of components above the weight cutoff), all retained points, their (row, component)
+    indices and the modal count.  Both point sets are (weight, rate) pairs, *not* yet in log space."""
     burn, wcutoff, weights, rates, keep = _filtered(gibbs)
     lens = keep.sum(axis=1)
     lmode = int(_mode(lens))
@@ -42,11 +40,30 @@ def cluster(gibbs, method='GaussianMixture', device=None, **kwargs):
     train = np.stack((weights[train_rows][keep[train_rows]], rates[train_rows][keep[train_rows]]), axis=1)
     rows, comps = np.where(keep)
     data = np.stack((weights[rows, comps], rates[rows, comps]), axis=1)
+    return train, data, rows, comps, lmode
 
-    model = getattr(mixture, method)(**kwargs)
+
+def cluster(gibbs, method='GaussianMixture', device=None, gmm_device=None, **kwargs):
+    """Cluster the retained (weight, rate) samples in log space and accumulate, per datum,
+    how often its label fell in each cluster (gibbs.py:221-273).  ``device``: GPU index to run the
+    accumulation on (``engine.pindicator_counts``, same integers); None keeps it in NumPy.
+    ``gmm_device``: GPU index to fit the mixture on (:mod:`basicrta_b200.gmm`) instead of
+    scikit-learn; only for ``method='GaussianMixture'``."""
+    train, data, rows, comps, lmode = cluster_inputs(gibbs)
+    if gmm_device is not None and method == 'GaussianMixture':
+        from .gmm import GaussianMixture
+        model = GaussianMixture(device=gmm_device, **kwargs)
+    else:
+        from sklearn import mixture
+        model = getattr(mixture, method)(**kwargs)
     model.fit(np.log(train))
     labels = model.predict(np.log(data))
+    return _accumulate(gibbs, labels, rows, comps, lmode, device)
 
+
+def _accumulate(gibbs, labels, rows, comps, lmode, device):
+    """gibbs.py:259-273: per-datum cluster membership frequencies from the stored label rows."""
+    burn = gibbs.burnin // gibbs.g
     resident = getattr(gibbs, '_device_indicator', None)     # Gibbs.run(keep_indicator_on_device=True)
     if gibbs.indicator is not None:
         indicator = gibbs.indicator[burn:]
@@ -98,14 +115,18 @@ def sort_labels(gibbs):
     return sorts[labels], presorts
 
 
-def process_gibbs(gibbs, save=True, device=None):
-    """gibbs.py:275-308 without figures.  ``device``: see :func:`cluster`."""
+def process_gibbs(gibbs, save=True, device=None, gmm_device=None, _labels=None):
+    """gibbs.py:275-308 without figures.  ``device`` / ``gmm_device``: see :func:`cluster`; ``_labels``: mixture
+    labels of the retained samples already fitted elsewhere (:func:`reprocess_batch`)."""
     burn, wcutoff, weights, rates, keep = _filtered(gibbs)
     rows, comps = np.where(keep)
     iteration = np.arange(gibbs.burnin, gibbs.niter + 1, gibbs.g)[rows] // gibbs.g
     lmode = int(_mode(keep.sum(axis=1)))
 
-    cluster(gibbs, n_init=117, n_components=lmode, device=device)
+    if _labels is None:
+        cluster(gibbs, n_init=117, n_components=lmode, device=device, gmm_device=gmm_device)
+    else:
+        _accumulate(gibbs, _labels, rows, comps, lmode, device)
     labels, presorts = sort_labels(gibbs)
     pr = gibbs.processed_results
     pr.labels = labels
@@ -115,6 +136,29 @@ def process_gibbs(gibbs, save=True, device=None):
     estimate_params(gibbs)
     if save:
         gibbs.save()
+
+
+def reprocess_batch(gibbs_list, device=0, n_init=117, seed=None, save=True, pindicator_on_device=True):
+    """``ProcessProtein.reprocess`` (basicrta/cluster.py:54-76: ``process_gibbs`` of every residue over a process
+    pool) with the mixture fits of ALL residues in one launch: 117 restarts x every residue = one CTA each
+    (``gmm.fit_batch``), one ``predict`` launch, then the per-residue tail of ``process_gibbs``.  A residue whose
+    fit fails the way scikit-learn's would (``ValueError``) is skipped like cluster.py:46 does; returns the list
+    of residues processed."""
+    import zlib
+
+    from . import gmm
+    inputs = [cluster_inputs(g) for g in gibbs_list]
+    ids = [zlib.crc32(f'{g.residue}|{g.cutoff}'.encode()) & 0xFFFFFFFF for g in gibbs_list]
+    fits = gmm.fit_batch([np.log(i[0]) for i in inputs], [i[4] for i in inputs], n_init=n_init, seed=seed,
+                         device=device, problem_ids=ids)
+    labels = gmm.predict_batch([np.log(i[1]) for i in inputs], fits, device=device)
+    done = []
+    for g, f, lab in zip(gibbs_list, fits, labels):
+        if f.error is not None:
+            continue
+        process_gibbs(g, save=save, device=device if pindicator_on_device else None, _labels=lab)
+        done.append(g)
+    return done
 
 
 def estimate_params(gibbs):

@@ -295,6 +295,62 @@ def api_leg(all_ticks, ncomp, niter, n_gpu, where):
             'dir': where}
 
 
+def posterior_cloud(r, rows=1000):
+    """Retained (log weight, log rate) samples shaped like residue r of C2 after sampling: 2-4 clusters, one per
+    true component, `rows` posterior rows each (what Gibbs.cluster feeds the mixture model, gibbs.py:238-252)."""
+    rng = np.random.default_rng(77000 + r)
+    m = int(rng.integers(2, 5))
+    lr = np.sort(rng.uniform(np.log(1e-3), np.log(10.0), m))[::-1] + np.arange(m)[::-1] * 0.5
+    w = np.sort(rng.dirichlet(np.ones(m)))[::-1]
+    pts = []
+    for k in range(m):
+        a = np.log(w[k]) + 0.05 / np.sqrt(w[k]) * rng.standard_normal(rows)
+        b = lr[k] + 0.04 / np.sqrt(w[k]) * rng.standard_normal(rows) + 0.3 * (a - np.log(w[k]))
+        pts.append(np.stack((a, b), axis=1))
+    x = np.concatenate(pts)
+    return x[rng.permutation(len(x))], m
+
+
+def gmm_leg(device, n_res=N_RESIDUES, n_init=117, cpu_residues=2):
+    """the mixture fits of process_gibbs for every residue of the sweep (n_init = 117,
+    gibbs.py:296) as one batch on the GPU, host arrays in, fitted parameters + labels out (wall clock), beside
+    scikit-learn -- the reference's own implementation -- on a bounded sample of the same problems."""
+    from basicrta_b200 import gmm
+    clouds = [posterior_cloud(r) for r in range(n_res)]
+    xs, ks = [c[0] for c in clouds], [c[1] for c in clouds]
+    gmm.fit_batch(xs[:8], ks[:8], n_init=4, seed=1, device=device)                 # module load, allocator
+    best = 1e30
+    for rep in range(2):
+        t0 = time.perf_counter()
+        fits = gmm.fit_batch(xs, ks, n_init=n_init, seed=20241109, device=device, problem_ids=np.arange(n_res))
+        labels = gmm.predict_batch(xs, fits, device=device)
+        best = min(best, time.perf_counter() - t0)
+    out = {'residues': n_res, 'n_init': n_init, 'points': int(sum(len(x) for x in xs)), 'wall_s': best,
+           'fits_per_s': n_res * n_init / best, 'failed': int(sum(f.error is not None for f in fits)),
+           'not_converged': int(sum(not f.converged for f in fits)),
+           'what': 'gmm.fit_batch + predict_batch: NumPy points in, parameters and labels out; one CTA per (residue, restart)'}
+    try:
+        from sklearn.mixture import GaussianMixture
+        t0 = time.perf_counter()
+        worst, agree = 0.0, 1.0
+        for r in range(cpu_residues):
+            sk = GaussianMixture(n_components=ks[r], n_init=n_init, random_state=r).fit(xs[r])
+            worst = max(worst, abs(sk.lower_bound_ - fits[r].lower_bound))
+            a, b = np.argsort(fits[r].means[:, 1]), np.argsort(sk.means_[:, 1])
+            ra, rb = np.empty(ks[r], int), np.empty(ks[r], int)
+            ra[a], rb[b] = np.arange(ks[r]), np.arange(ks[r])
+            agree = min(agree, float(np.mean(ra[labels[r]] == rb[sk.predict(xs[r])])))
+        cpu_s = (time.perf_counter() - t0) / cpu_residues
+        out['cpu_baseline'] = {'kind': 'reference', 'cores': 1, 's_per_residue': cpu_s,
+                               'sample': f'scikit-learn GaussianMixture(n_init={n_init}) on residues 0..{cpu_residues - 1} '
+                                         'of the same problems, one core (the reference fans residues over a process pool)',
+                               'extrapolated_wall_s_one_core': cpu_s * n_res,
+                               'max_lower_bound_difference': worst, 'min_label_agreement': agree}
+    except ImportError:
+        pass
+    return out
+
+
 def c4_leg(torch, dist, rank, world, local, niter):
     """The giant single residue on `world` GPUs (one rank per GPU): its times sharded over the ranks, integer
     (n_k, sum tick_k) exchanged inside the persistent kernels over NVLink every iteration.  Returns on rank 0:
@@ -519,6 +575,7 @@ def run_b200_arm(args):
                 if os.path.isdir(where) and shutil.disk_usage(where).free > 3 * label_bytes * world:
                     api[name] = api_leg(all_ticks, ncomp, niter, world, where)
             extras['e2e_api'] = api
+            extras['gmm'] = gmm_leg(local)
         if world > 1:
             dist.barrier(group=cpu_group)
 
@@ -587,6 +644,8 @@ def run_b200_arm(args):
                                'runs': api}
         if 'c4' in extras:
             line['c4'] = extras['c4']
+        if 'gmm' in extras:
+            line['gmm'] = extras['gmm']
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -602,9 +661,12 @@ def main():
     ap.add_argument('--residues', type=int, default=N_RESIDUES, help='developer knob; default = the named config')
     ap.add_argument('--niter', type=int, default=None, help='developer knob; default = the named config')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--skip-legs', action='store_true', help='developer knob: no e2e_api / c4 legs')
+    ap.add_argument('--skip-legs', action='store_true', help='developer knob: no e2e_api / c4 / gmm legs')
+    ap.add_argument('--only-gmm', action='store_true', help='developer knob: run the gmm leg alone and print it')
     args = ap.parse_args()
-    if args.impl == 'reference':
+    if args.only_gmm:
+        print(json.dumps({'gmm': gmm_leg(0)}))
+    elif args.impl == 'reference':
         run_reference_arm(args)
     else:
         run_b200_arm(args)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BRTA_ABI_VERSION 5
+#define BRTA_ABI_VERSION 6
 
 /* compile-time geometry of the sampler kernel */
 #ifndef BRTA_THREADS
@@ -263,6 +263,48 @@ int brta_mufu_probe(float* sink_dev, int blocks, int iters, void* stream);
 int brta_pindicator_counts(const uint8_t* indicator, int64_t row_stride, int32_t n_rows, int32_t n_data,
                            const int8_t* cluster_of, int32_t ncomp, int32_t n_clusters,
                            int32_t* counts, void* stream);
+
+/* Gaussian-mixture clustering of the retained (log weight, log rate) posterior samples -- the
+ * sklearn.mixture.GaussianMixture(n_init=117, n_components=lmode).fit of Gibbs.cluster / process_gibbs
+ * (basicrta/gibbs.py:255-256, 296), batched over residues ("problems") and restarts: one CTA per
+ * (problem, restart).  covariance_type='full', two features, float64.  Initialisation = greedy k-means++ and
+ * Lloyd iterations (scikit-learn's rule: squared centre shift <= kmeans_tol * mean(var(X))) on the Philox
+ * stream (seed; draw, restart, problem_id), then an M step on the one-hot responsibilities; or, with
+ * init_params, injected initial parameters (parity tests).  EM as scikit-learn's BaseMixture.fit_predict:
+ * lower bound = mean log-sum-exp before the M step, stop at |change| < tol or after max_iter iterations.
+ * The caller picks the restart (first strictly largest lower_bound; a restart with status
+ * BRTA_GMM_ILL_DEFINED is where scikit-learn raises ValueError).  Parameter blocks are
+ * [BRTA_GMM_MAX_COMPONENTS][6] doubles per (problem, restart): weight, mean x, mean y, cov xx, cov xy, cov yy.
+ * All pointers are device pointers. */
+#define BRTA_GMM_MAX_COMPONENTS 16
+#define BRTA_GMM_THREADS       128
+#define BRTA_GMM_MAX_POINTS  26624   /* per problem: 8 B of shared memory per point during the seeding */
+#define BRTA_GMM_CONVERGED       0
+#define BRTA_GMM_NOT_CONVERGED   1   /* max_iter reached (scikit-learn warns) */
+#define BRTA_GMM_ILL_DEFINED     2   /* a covariance lost positive definiteness (scikit-learn raises ValueError) */
+typedef struct brta_gmm_batch {
+    int32_t n_problems, n_init, max_iter, kmeans_max_iter;   /* sklearn defaults: n_init 1 (the reference: 117), 100, 300 */
+    int32_t max_points;                                      /* largest point count of a problem                        */
+    int32_t class_mask;              /* which component-count classes occur: bit 0: 1-4, bit 1: 5-8, bit 2: 9-16; 0: all */
+    double tol, reg_covar, kmeans_tol;                       /* sklearn defaults: 1e-3, 1e-6, 1e-4                      */
+    uint64_t seed;
+    const double*   x;               /* [sum M_p][2] points of all problems, concatenated                      */
+    const int64_t*  offsets;         /* [n_problems + 1] first point of each problem                           */
+    const int32_t*  n_components;    /* [n_problems], 1..BRTA_GMM_MAX_COMPONENTS, <= M_p                       */
+    const uint32_t* problem_id;      /* [n_problems] Philox counter word of each problem; NULL: its index      */
+    const double*   init_params;     /* optional [n_problems][n_init][16][6]: skip the k-means initialisation  */
+    double*  lower_bound;            /* [n_problems][n_init]; NaN for an ill-defined restart                    */
+    int32_t* n_iter;                 /* [n_problems][n_init] EM iterations run                                  */
+    int32_t* status;                 /* [n_problems][n_init] BRTA_GMM_*                                         */
+    double*  params;                 /* [n_problems][n_init][16][6] fitted parameters                           */
+    double*  init_out;               /* optional, same shape: the initial parameters the EM started from        */
+} brta_gmm_batch;
+int brta_gmm_fit_batch(const brta_gmm_batch* batch, void* stream);
+
+/* GaussianMixture.predict (gibbs.py:257): labels[i] = argmax_k log w_k + log N(x_i | mu_k, Sigma_k), first
+ * maximum on ties; params: [n_problems][16][6] (one block per problem), labels: uint8 [sum M_p]. */
+int brta_gmm_predict(const double* x, const int64_t* offsets, int32_t n_problems, int32_t max_points,
+                     const int32_t* n_components, const double* params, uint8_t* labels, void* stream);
 
 /* Test hook for the posterior update (gibbs.py:210-211 calls numpy's Generator.dirichlet / .gamma):
  * out[i] = log2 of a Gamma(shapes[i % n_shapes], 1) variate drawn by the sampler's own device

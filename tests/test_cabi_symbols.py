@@ -44,7 +44,8 @@ def _struct_fields(name):
 
 
 @pytest.mark.parametrize('cname,cls', [('brta_caps', _cabi.Caps), ('brta_launch_info', _cabi.LaunchInfo),
-                                       ('brta_task', _cabi.Task), ('brta_batch', _cabi.Batch)])
+                                       ('brta_task', _cabi.Task), ('brta_batch', _cabi.Batch),
+                                       ('brta_gmm_batch', _cabi.GmmBatch)])
 def test_ctypes_mirror_matches_header(cname, cls):
     assert _struct_fields(cname) == [f[0] for f in cls._fields_]
 
@@ -58,6 +59,10 @@ def test_constants_match_header():
     assert int(macro('BRTA_MAILBOX_MAX_TEAM')) == _cabi.MAILBOX_MAX_TEAM
     for flag in ('EXACT', 'INJECT_COEF', 'INJECT_U', 'TRACE', 'NO_TABLE', 'CTAS3'):
         assert int(macro('BRTA_FLAG_' + flag)) == getattr(_cabi, 'FLAG_' + flag)
+    assert int(macro('BRTA_GMM_MAX_COMPONENTS')) == _cabi.GMM_MAX_COMPONENTS
+    assert int(macro('BRTA_GMM_MAX_POINTS')) == _cabi.GMM_MAX_POINTS
+    assert [int(macro('BRTA_GMM_' + n)) for n in ('CONVERGED', 'NOT_CONVERGED', 'ILL_DEFINED')] == \
+        [_cabi.GMM_CONVERGED, _cabi.GMM_NOT_CONVERGED, _cabi.GMM_ILL_DEFINED]
     from basicrta_b200.plan import TASK_DTYPE
     assert TASK_DTYPE.itemsize == C.sizeof(_cabi.Task)
     assert list(TASK_DTYPE.names) == [f[0] for f in _cabi.Task._fields_]
@@ -77,6 +82,16 @@ def test_argument_errors_do_not_need_a_gpu():
     assert lib.brta_pindicator_counts(p, 4, 2, 8, p, 15, 3, p, None) == -3   # row_stride < n_data: BRTA_E_RANGE
     assert lib.brta_pindicator_counts(p, 8, 2, 8, p, 15, 33, p, None) == -2  # n_clusters > 32
     assert lib.brta_pindicator_counts(p, 8, 0, 8, p, 15, 3, p, None) == 0    # nothing to do
+    assert lib.brta_gmm_fit_batch(None, None) == -1
+    g = _cabi.GmmBatch()
+    assert lib.brta_gmm_fit_batch(C.byref(g), None) == -1                 # NULL pointers inside
+    for f in ('x', 'offsets', 'n_components', 'lower_bound', 'n_iter', 'status', 'params'):
+        setattr(g, f, p.value)
+    g.n_init, g.max_points = 1, _cabi.GMM_MAX_POINTS + 1
+    assert lib.brta_gmm_fit_batch(C.byref(g), None) == -3                 # too many points: BRTA_E_RANGE
+    g.max_points, g.n_problems = 10, 0
+    assert lib.brta_gmm_fit_batch(C.byref(g), None) == 0                  # nothing to do
+    assert lib.brta_gmm_predict(None, None, 0, 0, None, None, None, None) == -1
 
 
 def test_product_fails_loudly_without_cuda():
