@@ -27,7 +27,11 @@ def _case(rng, S, N, K, C, keep=0.6):
 
 
 @pytest.mark.parametrize('S,N,K,C', [(1, 1, 2, 1), (7, 257, 15, 3), (129, 5000, 15, 6), (300, 1031, 30, 32),
-                                     (1000, 20000, 15, 4)])
+                                     (1000, 20000, 15, 4),
+                                     # every row alignment class (N mod 4), more rows than one chunk of byte
+                                     # counters, and 1 / 2 / 4 counter words per datum in the aligned-class kernel
+                                     (1300, 4096, 15, 4), (1001, 4097, 15, 4), (1001, 4098, 30, 6), (517, 4099, 15, 12),
+                                     (260, 3000, 30, 12), (9, 3, 64, 4), (2, 70001, 15, 2)])
 def test_counts_match_numpy_and_reference_loop(S, N, K, C):
     from basicrta_b200.engine import pindicator_counts
     from basicrta_b200.postprocess import pindicator_counts_host
@@ -46,6 +50,20 @@ def test_counts_match_numpy_and_reference_loop(S, N, K, C):
     lut = np.full((S, K), -1, dtype=np.int8)
     lut[rows, comps] = labels
     np.testing.assert_array_equal(pindicator_counts(big[:, :N], lut, C), host)
+
+
+def test_both_kernels_give_the_same_counts(monkeypatch):
+    """The aligned-class kernel (default where the table fits) against the generic one (developer knob)."""
+    from basicrta_b200.engine import pindicator_counts
+    rng = np.random.default_rng(5)
+    indicator, rows, comps, labels = _case(rng, 1003, 30011, 15, 4)
+    indicator[::7, ::5] = 77                                               # labels beyond ncomp: never counted
+    lut = np.full((1003, 15), -1, dtype=np.int8)
+    lut[rows, comps] = labels
+    fast = pindicator_counts(indicator, lut, 4)
+    monkeypatch.setenv('BRTA_PINDICATOR_GENERIC', '1')
+    np.testing.assert_array_equal(pindicator_counts(indicator, lut, 4), fast)
+    assert fast.sum() == (lut[np.arange(1003)[:, None], np.minimum(indicator, 14)] >= 0)[indicator < 15].sum()
 
 
 def test_out_of_range_labels_and_empty_rows_are_ignored():

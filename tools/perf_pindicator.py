@@ -45,5 +45,5 @@ try:
     peak = float(json.load(open(os.path.join(os.path.dirname(__file__), '..', 'MEASURED_PEAKS.json')))['hbm_gbs'])
 except Exception:
     pass
-print(f'S={S} N={N} K={K} C={NC}: {best:.3f} ms, {nbytes / best / 1e6:.1f} GB/s algorithmic '
+print(('generic ' if os.environ.get('BRTA_PINDICATOR_GENERIC') else 'class   ') + f'S={S} N={N} K={K} C={NC}: {best:.3f} ms, {nbytes / best / 1e6:.1f} GB/s algorithmic '
       f'({nbytes / best / 1e6 / peak:.3f} of {peak:.0f} GB/s), {S * N / best / 1e6:.1f} G labels/s')
