@@ -17,6 +17,7 @@ schedule gives every chain a *team* of CTAs sized in proportion to its cost
 Pure NumPy, no GPU needed: the host logic is covered by the CPU test-suite.
 """
 import heapq
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -24,7 +25,7 @@ import numpy as np
 TASK_DTYPE = np.dtype([('chain', np.int32), ('team_size', np.int32), ('team_rank', np.int32),
                        ('quad_begin', np.int32), ('quad_count', np.int32), ('order', np.int32)])
 
-MIN_SLICE_QUADS = 32        # a CTA has 128 threads; below this most of them idle
+MIN_SLICE_QUADS = int(os.environ.get('BRTA_MIN_SLICE_QUADS', 32))   # a CTA has 128 threads; below this most of them idle
 DEFAULT_OVERHEAD_QUADS = 192.0   # rendezvous + posterior draw per iteration, in quad-times
 
 
