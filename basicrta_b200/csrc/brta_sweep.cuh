@@ -935,9 +935,15 @@ __device__ BRTA_SERIAL_ATTR void serial_part(const SweepParams& prm, const brta_
         b.trace_nk[o] = (int64_t)tot_c;
         b.trace_tk[o] = (int64_t)tot_s;
     }
-    // next iteration skips the most populated label in the atomics
+    // next iteration skips, in the atomics, the label that is most populated IN THIS CTA'S SLICE (the chain is in
+    // ascending-tick order: later slices are dominated by slower components than the chain as a whole, and a
+    // warp whose lanes all add to one shared-memory address serialises).  Any choice gives the same integers.
+#ifndef BRTA_LOCAL_DOM
+#define BRTA_LOCAL_DOM 1
+#endif
     {
-        const unsigned keyv = own ? ((tot_c << 5) | (unsigned)(31 - lane)) : 0u;
+        const unsigned dom_src = BRTA_LOCAL_DOM ? cnt : tot_c;
+        const unsigned keyv = own ? ((dom_src << 5) | (unsigned)(31 - lane)) : 0u;
         dom = 31 - (int)(__reduce_max_sync(FULL, keyv) & 31u);
         if (lane == 0) *s_dom = dom;
     }
