@@ -241,6 +241,25 @@ __device__ __forceinline__ void red_shared_stats(uint32_t cnt_addr, uint32_t tic
                  "red.shared.add.u32 [%0+128], %1;"
                  :: "r"(cnt_addr), "r"(tick_bits) : "memory");
 }
+// The same, for a datum whose label offset may be the dominant one (which is not counted).
+// BRTA_STATS_MODE 0: `if (off != dom_off) red_shared_stats(...)`.  ptxas turns that into a divergent branch per
+//   datum (BSSY, BRA, the address rematerialised inside the branch, two ATOMS, BSYNC): nine issue slots per datum
+//   whenever one lane of the warp is active, four otherwise.  (Explicitly predicated `@p red.shared` is no way
+//   out: ptxas wraps EACH predicated shared-memory atomic in its own branch region.)
+// BRTA_STATS_MODE 2: no branch -- a dominant label adds to a per-lane dummy slot (block `par + 2` of s_stat, 32
+//   different banks, never read) instead of being skipped: select + two unconditional atomics.
+#ifndef BRTA_STATS_MODE
+#define BRTA_STATS_MODE 2
+#endif
+__device__ __forceinline__ void red_shared_stats_ne(uint32_t off, uint32_t dom_off, uint32_t stat_addr, uint32_t tick_bits)
+{
+#if BRTA_STATS_MODE == 2
+    const uint32_t dummy = stat_addr + 512u + 4u * (threadIdx.x & 31u);
+    red_shared_stats(off != dom_off ? stat_addr + off : dummy, tick_bits);
+#else
+    if (off != dom_off) red_shared_stats(stat_addr + off, tick_bits);
+#endif
+}
 // ---- memoised cumulative rows ---------------------------------------------------------------
 // The cumulative sums of a datum depend on its tick only, and residence times are small
 // integers with huge multiplicities (half of a typical slice holds fewer than a dozen distinct
@@ -428,9 +447,8 @@ __device__ __forceinline__ void sweep_quad(const uint4 tk, const float4 f12, con
             if (i0 + d >= n_data) labs[d] = dom;
     }
 #pragma unroll
-    for (int d = 0; d < 4; ++d)
-        if (labs[d] != dom)                                // ATOMS cost scales with the active lanes
-            red_shared_stats(stat_addr + 4u * (uint32_t)labs[d], tis[d]);
+    for (int d = 0; d < 4; ++d)                            // ATOMS cost scales with the active lanes
+        red_shared_stats_ne(4u * (uint32_t)labs[d], 4u * (uint32_t)dom, stat_addr, tis[d]);
     if (SAVE) {                                            // 1 iteration in `thin`: dense [S,N] bytes
 #pragma unroll
         for (int d = 0; d < 4; ++d)
@@ -476,7 +494,7 @@ __device__ __forceinline__ void sweep_served(uint32_t slice_addr, int q0, int qb
     for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int d = 0; d < 4; ++d)
-            if (off[u][d] != dom_off) red_shared_stats(stat_addr + off[u][d], tis[u][d]);
+            red_shared_stats_ne(off[u][d], dom_off, stat_addr, tis[u][d]);
     if (SAVE) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -1028,7 +1046,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
     __shared__ float s_hyp[2][32];                         // prior shapes of the gammas a lane draws (per pass)
     __shared__ float s_rhb[32];                            // prior rate of the rate gamma (gibbs.py:174)
     // this CTA's statistics, [parity][0..31] n_k, [parity][32..63] tick sums (fit 32 bits: host-checked)
-    __shared__ __align__(16) unsigned s_stat[2][64];
+    __shared__ __align__(16) unsigned s_stat[4][64];        // blocks 2, 3: per-lane dummy slots of the dominant label (write-only)
     __shared__ __align__(16) float s_table[TABLE_FLOATS + 32];  // memoised cumulative rows of the running iteration (+ probe overrun)
     const uint32_t stat_addr0 = opaque_u32((uint32_t)__cvta_generic_to_shared(&s_stat[0][0]));
     const uint32_t slice_addr = opaque_u32((uint32_t)__cvta_generic_to_shared(smem_raw));
@@ -1176,7 +1194,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
             PHASE_MARK(1);
             const int par = j & 1;
             const int dom = s_dom;
-            const uint32_t stat_addr = stat_addr0 + 256u * (uint32_t)par;
+            const uint32_t stat_addr = opaque_u32(stat_addr0 + 256u * (uint32_t)par);   // opaque: not rematerialised per datum
             const bool save = (j % thin == 0);
             const int row = j / thin - 1;
             const float4* const u_row = inject_u
