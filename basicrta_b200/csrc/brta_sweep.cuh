@@ -246,7 +246,7 @@ __device__ __forceinline__ void red_shared_stats(uint32_t cnt_addr, uint32_t tic
 //   datum (BSSY, BRA, the address rematerialised inside the branch, two ATOMS, BSYNC): nine issue slots per datum
 //   whenever one lane of the warp is active, four otherwise.  (Explicitly predicated `@p red.shared` is no way
 //   out: ptxas wraps EACH predicated shared-memory atomic in its own branch region.)
-// BRTA_STATS_MODE 2: no branch -- a dominant label adds to a per-lane dummy slot (block `par + 2` of s_stat, 32
+// BRTA_STATS_MODE 2: no branch -- a dominant label adds to a per-lane dummy slot (block 2 of s_stat, 32
 //   different banks, never read) instead of being skipped: select + two unconditional atomics.
 #ifndef BRTA_STATS_MODE
 #define BRTA_STATS_MODE 2
@@ -254,11 +254,31 @@ __device__ __forceinline__ void red_shared_stats(uint32_t cnt_addr, uint32_t tic
 __device__ __forceinline__ void red_shared_stats_ne(uint32_t off, uint32_t dom_off, uint32_t stat_addr, uint32_t tick_bits)
 {
 #if BRTA_STATS_MODE == 2
-    const uint32_t dummy = stat_addr + 512u + 4u * (threadIdx.x & 31u);
+    const uint32_t dummy = (stat_addr & ~256u) + 512u + 4u * (threadIdx.x & 31u);
     red_shared_stats(off != dom_off ? stat_addr + off : dummy, tick_bits);
 #else
     if (off != dom_off) red_shared_stats(stat_addr + off, tick_bits);
 #endif
+}
+// Statistics of the SERVED prefix: one atomic per datum instead of two.  Every tick of the prefix lies in the
+// window [lo, lo + rows) of the memoised rows, rows <= PACKED_MAX_ROWS = 256, so `tick - lo` fits 8 bits and
+// (1 << 20 | tick - lo) added to one 32-bit word counts the datum in bits 20-31 and sums its offset in bits
+// 0-19.  Eight accumulator sets per CTA (warp x position in the unrolled pair) keep both fields from
+// overflowing: a set sees at most (n_served / 256 + 1) * 128 data, i.e. <= 3968 (< 4096) for slices of up to
+// PACKED_MAX_QUADS quads, and 3968 * 255 < 2^20.  The lead warp unpacks: n += sum of counts,
+// sum of ticks += sum of offsets + lo * counts.  Shared-memory atomics are what limits the branch-free form
+// (BRTA_STATS_MODE 2), so halving them is what pays.  s_stat layout (512-byte aligned, 64 words per block):
+// blocks 0, 1 = (n_k, sum tick_k) of the two parities, block 2 = dummy slots, blocks 3-6 = the eight packed sets.
+#ifndef BRTA_PACKED_STATS
+#define BRTA_PACKED_STATS 1
+#endif
+constexpr int PACKED_MAX_ROWS = 256;
+constexpr int PACKED_MAX_QUADS = 7680;
+constexpr int STAT_BLOCKS = 7;
+__device__ __forceinline__ void red_shared_packed(uint32_t off, uint32_t dom_off, uint32_t set_addr, uint32_t dummy, uint32_t rel)
+{
+    const uint32_t a = off != dom_off ? set_addr + off : dummy;
+    asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(a), "r"(rel | (1u << 20)) : "memory");
 }
 // ---- memoised cumulative rows ---------------------------------------------------------------
 // The cumulative sums of a datum depend on its tick only, and residence times are small
@@ -273,6 +293,8 @@ __host__ __device__ constexpr int table_row_floats(int k) { return (k + 3) / 4 *
 // rows are laid out with an odd stride so that the same entry of neighbouring rows (what the lanes
 // of a warp read during the search) falls into different banks
 __host__ __device__ constexpr int table_row_stride(int k) { return table_row_floats(k) + 1; }
+// rows of the table: what fits, at most 256 (tick - lo of a served datum fits 8 bits: packed statistics)
+__host__ __device__ constexpr int table_rows_max(int k) { return TABLE_FLOATS / table_row_stride(k) < 256 ? TABLE_FLOATS / table_row_stride(k) : 256; }
 
 struct TableView {
     uint32_t addr;           // shared-window byte address of row 0; row r = cumulative sums of tick lo + r
@@ -490,11 +512,23 @@ __device__ __forceinline__ void sweep_served(uint32_t slice_addr, int q0, int qb
             off[u][d] = search_row<K>(tis[u][d], fs[u][d], tab, total);
         }
     const uint32_t dom_off = 4u * (uint32_t)dom;
+#if BRTA_PACKED_STATS
+    static_assert(STRIDE == THREADS && U <= 2, "packed statistics: set = 2 * warp + u");
+    const uint32_t stat_base = stat_addr & ~256u;
+    const uint32_t dummy = stat_base + 512u + 4u * (threadIdx.x & 31u);
+    const uint32_t set0 = stat_base + 768u + 256u * (threadIdx.x >> 5);
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+            red_shared_packed(off[u][d], dom_off, set0 + 128u * u, dummy, tis[u][d] - tab.lo);
+#else
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int d = 0; d < 4; ++d)
             red_shared_stats_ne(off[u][d], dom_off, stat_addr, tis[u][d]);
+#endif
     if (SAVE) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -761,7 +795,7 @@ __device__ __forceinline__ void st_relaxed_sys_v2(unsigned long long* p, unsigne
 template <int K>
 __device__ BRTA_SERIAL_ATTR void serial_part(const SweepParams& prm, const brta_task task, const int j, const int par,
                                              int dom, const unsigned slice_n, const unsigned long long slice_t,
-                                             const bool save, const int row, const int rows,
+                                             const bool save, const int row, const int rows, const unsigned tick_lo,
                                              const uint32_t key0, const uint32_t key1,
                                              unsigned (*s_stat)[64], float2* s_coef, float (*s_hyp)[32], const float* s_rhb,
                                              int* s_dom, unsigned* s_bad, unsigned* s_abort PHASE_LEAD_PARAM)
@@ -801,6 +835,20 @@ __device__ BRTA_SERIAL_ATTR void serial_part(const SweepParams& prm, const brta_
     unsigned long long sum = s_stat[par][32 + lane];
     s_stat[par][lane] = 0;                                 // ready for iteration j + 2
     s_stat[par][32 + lane] = 0;
+#if BRTA_PACKED_STATS
+    {   // the served prefix's packed sets: bits 20-31 count, bits 0-19 sum of (tick - tick_lo)
+        unsigned pc = 0, ps = 0;
+#pragma unroll
+        for (int set = 0; set < 8; ++set) {
+            const unsigned w = s_stat[3 + (set >> 1)][(set & 1) * 32 + lane];
+            s_stat[3 + (set >> 1)][(set & 1) * 32 + lane] = 0;
+            pc += w >> 20;
+            ps += w & 0xfffffu;
+        }
+        cnt += pc;
+        sum += (unsigned long long)ps + (unsigned long long)pc * tick_lo;
+    }
+#endif
     {
         const unsigned oc = __reduce_add_sync(FULL, cnt);
         const unsigned os = __reduce_add_sync(FULL, (unsigned)sum);
@@ -1046,7 +1094,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
     __shared__ float s_hyp[2][32];                         // prior shapes of the gammas a lane draws (per pass)
     __shared__ float s_rhb[32];                            // prior rate of the rate gamma (gibbs.py:174)
     // this CTA's statistics, [parity][0..31] n_k, [parity][32..63] tick sums (fit 32 bits: host-checked)
-    __shared__ __align__(16) unsigned s_stat[4][64];        // blocks 2, 3: per-lane dummy slots of the dominant label (write-only)
+    __shared__ __align__(512) unsigned s_stat[STAT_BLOCKS][64];   // layout: see red_shared_packed
     __shared__ __align__(16) float s_table[TABLE_FLOATS + 32];  // memoised cumulative rows of the running iteration (+ probe overrun)
     const uint32_t stat_addr0 = opaque_u32((uint32_t)__cvta_generic_to_shared(&s_stat[0][0]));
     const uint32_t slice_addr = opaque_u32((uint32_t)__cvta_generic_to_shared(smem_raw));
@@ -1127,7 +1175,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
         my_lo = __reduce_min_sync(FULL, my_lo);
         my_hi = __reduce_max_sync(FULL, my_hi);
         if (lane == 0) { s_red_n[warp] = my_n; s_red_t[warp] = my_t; s_red_lo[warp] = my_lo; s_red_hi[warp] = my_hi; }
-        if (tid < 64) { s_stat[0][tid] = 0; s_stat[1][tid] = 0; }
+        for (int x = tid; x < STAT_BLOCKS * 64; x += THREADS) (&s_stat[0][0])[x] = 0;
         if (tid == 0) { s_bad = 0; s_abort = 0; s_dom = 0; s_next[0] = 0; s_next[1] = 0; }
         if (warp == 0) {
             // coefficients of the first iteration of this launch and the priors: lane = component
@@ -1169,12 +1217,14 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
         // memoised rows cover ticks lo .. lo + table_rows - 1 of this slice
         int table_rows = 0;
         if (!(b.flags & BRTA_FLAG_NO_TABLE) && tick_lo <= tick_hi)
-            table_rows = (int)min((unsigned)(TABLE_FLOATS / table_row_stride(K)), tick_hi - tick_lo + 1u);
+            table_rows = (int)min((unsigned)table_rows_max(K), tick_hi - tick_lo + 1u);
         TableView tab;
         tab.addr = table_addr;
         tab.lo = tick_lo;
         tab.limit = table_rows > 0 ? tick_lo + (unsigned)table_rows : 0u;
-        const int n_served = served_prefix(smem_raw, ticks16, nq, qb, n_data, tab.limit, s_red_lo);
+        // (a slice too long for the packed statistics -- developer builds with fewer CTAs per SM -- takes the general loop)
+        const int n_served = (!BRTA_PACKED_STATS || nq <= PACKED_MAX_QUADS)
+                                 ? served_prefix(smem_raw, ticks16, nq, qb, n_data, tab.limit, s_red_lo) : 0;
 
         unsigned long long busy_cycles = 0;                // schedule feedback: iteration start -> statistics complete
         PHASE_DECL
@@ -1214,7 +1264,7 @@ gibbs_sweep_kernel(const __grid_constant__ SweepParams prm)
             if (b.task_cycles && 2 * (j - j_begin) > j_end - j_begin) busy_cycles += (unsigned long long)(clock64() - iter_t0);
 
             if (warp == lead)
-                serial_part<K>(prm, task, j, par, dom, slice_n, slice_t, save, row, rows, key0, key1,
+                serial_part<K>(prm, task, j, par, dom, slice_n, slice_t, save, row, rows, tick_lo, key0, key1,
                                s_stat, s_coef, s_hyp, s_rhb, &s_dom, &s_bad, &s_abort PHASE_LEAD_ARG);
             __syncthreads();                               // B: coefficients of iteration j + 1 are published
             PHASE_MARK(4);

@@ -11,13 +11,14 @@ other every iteration, hence slices must take equal time, not hold equal counts.
 import numpy as np
 
 TABLE_FLOATS = 4096                      # must match TABLE_FLOATS in csrc/brta_gibbs.cu
+MAX_ROWS = 256                           # table_rows_max of csrc/brta_sweep.cuh: tick - lo fits 8 bits (packed statistics)
 COST_SERVED = 0.5                        # quad-times of a quad read from the table (measured optimum on B200)
 COST_DIRECT = 1.0                        # quad-times of a recomputed quad
 
 
 def table_rows(ncomp):
     """Rows of the kernel's table: TABLE_FLOATS / table_row_stride(K) (odd stride, see brta_gibbs.cu)."""
-    return TABLE_FLOATS // ((int(ncomp) + 3) // 4 * 4 + 1)
+    return min(TABLE_FLOATS // ((int(ncomp) + 3) // 4 * 4 + 1), MAX_ROWS)
 
 
 class ChainCost:
