@@ -263,9 +263,8 @@ __device__ __forceinline__ void red_shared_stats_ne(uint32_t off, uint32_t dom_o
 // Statistics of the SERVED prefix: one atomic per datum instead of two.  Every tick of the prefix lies in the
 // window [lo, lo + rows) of the memoised rows, rows <= PACKED_MAX_ROWS = 256, so `tick - lo` fits 8 bits and
 // (1 << 20 | tick - lo) added to one 32-bit word counts the datum in bits 20-31 and sums its offset in bits
-// 0-19.  Eight accumulator sets per CTA (warp x position in the unrolled pair) keep both fields from
-// overflowing: a set sees at most (n_served / 256 + 1) * 128 data, i.e. <= 3968 (< 4096) for slices of up to
-// PACKED_MAX_QUADS quads, and 3968 * 255 < 2^20.  The lead warp unpacks: n += sum of counts,
+// 0-19.  Eight accumulator sets per CTA keep both fields from overflowing: a set sees an eighth of the served
+// data, i.e. <= 3968 (< 4096) for slices of up to PACKED_MAX_QUADS quads, and 3968 * 255 < 2^20.  The lead warp unpacks: n += sum of counts,
 // sum of ticks += sum of offsets + lo * counts.  Shared-memory atomics are what limits the branch-free form
 // (BRTA_STATS_MODE 2), so halving them is what pays.  s_stat layout (512-byte aligned, 64 words per block):
 // blocks 0, 1 = (n_k, sum tick_k) of the two parities, block 2 = dummy slots, blocks 3-6 = the eight packed sets.
@@ -275,10 +274,20 @@ __device__ __forceinline__ void red_shared_stats_ne(uint32_t off, uint32_t dom_o
 constexpr int PACKED_MAX_ROWS = 256;
 constexpr int PACKED_MAX_QUADS = 7680;
 constexpr int STAT_BLOCKS = 7;
+// BRTA_PACKED_BY_LANE 0 (default): set = 2 * warp + position in the unrolled pair.  1: set = lane & 7 (every set
+// still sees an eighth of the data), so the lanes of a warp that add to the same component spread over eight
+// addresses -- measured: +3 % at 50 chains per GPU, -5 % at 100, -0.5 % on C2 (profiles/r2q_*): not adopted.
+#ifndef BRTA_PACKED_BY_LANE
+#define BRTA_PACKED_BY_LANE 0
+#endif
 __device__ __forceinline__ void red_shared_packed(uint32_t off, uint32_t dom_off, uint32_t set_addr, uint32_t dummy, uint32_t rel)
 {
+#if BRTA_STATS_MODE == 2
     const uint32_t a = off != dom_off ? set_addr + off : dummy;
     asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(a), "r"(rel | (1u << 20)) : "memory");
+#else
+    if (off != dom_off) asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(set_addr + off), "r"(rel | (1u << 20)) : "memory");
+#endif
 }
 // ---- memoised cumulative rows ---------------------------------------------------------------
 // The cumulative sums of a datum depend on its tick only, and residence times are small
@@ -516,12 +525,18 @@ __device__ __forceinline__ void sweep_served(uint32_t slice_addr, int q0, int qb
     static_assert(STRIDE == THREADS && U <= 2, "packed statistics: set = 2 * warp + u");
     const uint32_t stat_base = stat_addr & ~256u;
     const uint32_t dummy = stat_base + 512u + 4u * (threadIdx.x & 31u);
+#if BRTA_PACKED_BY_LANE
+    const uint32_t set0 = stat_base + 768u + 128u * (threadIdx.x & 7u);
+    constexpr uint32_t SET_STEP = 0u;
+#else
     const uint32_t set0 = stat_base + 768u + 256u * (threadIdx.x >> 5);
+    constexpr uint32_t SET_STEP = 128u;
+#endif
 #pragma unroll
     for (int u = 0; u < U; ++u)
 #pragma unroll
         for (int d = 0; d < 4; ++d)
-            red_shared_packed(off[u][d], dom_off, set0 + 128u * u, dummy, tis[u][d] - tab.lo);
+            red_shared_packed(off[u][d], dom_off, set0 + SET_STEP * u, dummy, tis[u][d] - tab.lo);
 #else
 #pragma unroll
     for (int u = 0; u < U; ++u)
