@@ -219,8 +219,8 @@ class ClockSampler:
 
 
 # ---- evidence from the committed ncu captures (profiles/README.md) ---------------------------------
-PROFILE_TRAFFIC = os.path.join(ROOT, 'profiles', 'r2_dram_bytes_bench.csv')
-PROFILE_FULL = os.path.join(ROOT, 'profiles', 'r2_ncu_full_selected_c2.csv')
+PROFILE_TRAFFIC = os.path.join(ROOT, 'profiles', 'r2z_dram_bytes_bench.csv')
+PROFILE_FULL = os.path.join(ROOT, 'profiles', 'r2z_ncu_full_selected_c2.csv')
 PROFILE_FULL_NITER = 300             # iterations of the launch captured in PROFILE_FULL (tools/perf.py 400 300)
 
 
@@ -614,7 +614,7 @@ def run_b200_arm(args):
                          'frac': per_gpu / peak, 'frac_executed': per_gpu * ex2_share / peak,
                          'issue_frac': None if ipu is None else ipu * per_gpu / issue_rate,
                          'traffic': profiled_traffic(config, len(all_ticks), niter, world),
-                         'traffic_unit': 'bytes per launch (ncu dram read + write, profiles/r2_dram_bytes_bench.csv); '
+                         'traffic_unit': 'bytes per launch (ncu dram read + write, profiles/r2z_dram_bytes_bench.csv); '
                                          f'algorithmic: {algo_bytes:.4g}',
                          'executed_ex2_share': ex2_share,
                          'note': 'per GPU.  frac: algorithmic units (1 ex2 per (datum, component) pair per iteration, SURVEY '
@@ -623,7 +623,7 @@ def run_b200_arm(args):
                                  'peak.  Data with equal ticks share memoised cumulative rows, so only executed_ex2_share of '
                                  'those ex2 are issued (frac_executed = the XU pipe\'s real load).  The limit the kernel '
                                  'runs into is instruction issue and dependent-instruction latency: issue_frac = executed '
-                                 'warp instructions per unit (ncu, profiles/r2_ncu_full_selected_c2.csv) x units/s over '
+                                 'warp instructions per unit (ncu, profiles/r2z_ncu_full_selected_c2.csv) x units/s over '
                                  '4 x SMs x clock.',
                          'hbm': {'achieved': algo_bytes / sec / 1e9, 'peak': hbm, 'unit': 'GB/s',
                                  'frac': algo_bytes / sec / 1e9 / hbm,
