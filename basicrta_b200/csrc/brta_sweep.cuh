@@ -887,6 +887,15 @@ __device__ BRTA_SERIAL_ATTR void serial_part(const SweepParams& prm, const brta_
         // the CTA that arrives LAST holds the GPU's totals and sends them to every GPU's mailbox over
         // NVLink as tagged 64-bit words {iteration | n_k}, {iteration | sum lo}, {iteration | sum hi}.
         const int buf = j % 3;
+        if (task.team_rank == 0) {
+            // recycle the buffer of iteration j + 1 BEFORE arriving for j.  Nobody adds to it earlier: a member
+            // starts j + 1 only after the arrive count of j is complete, which includes this arrive (ordered
+            // after these stores by the fence below).  Nobody still reads its old contents (iteration j - 2):
+            // this CTA is past iteration j - 1, so every member has posted j - 1, i.e. finished j - 2.
+            const int nxt = (j + 1) % 3;
+            ex_cnt[nxt * 32 + lane] = 0u;
+            ex_sum[nxt * 32 + lane] = 0ull;
+        }
         if (cnt != 0u) {
             atomicAdd(&ex_cnt[buf * 32 + lane], cnt);
             atomicAdd(&ex_sum[buf * 32 + lane], sum);
@@ -913,11 +922,6 @@ __device__ BRTA_SERIAL_ATTR void serial_part(const SweepParams& prm, const brta_
                     }
                 }
             }
-        }
-        if (task.team_rank == 0) {                         // recycle the buffer last read in j-1
-            const int old = (j + 2) % 3;
-            ex_cnt[old * 32 + lane] = 0u;
-            ex_sum[old * 32 + lane] = 0ull;
         }
     }
     // shape-independent half of the Marsaglia-Tsang trials, overlapped with the exchange
