@@ -106,3 +106,38 @@ def test_shard_bounds():
     assert shard_bounds(60001, 2) == [0, 7502, 15001]
     with pytest.raises(ValueError):
         shard_bounds(9, 8)
+
+
+def test_memo_table_geometry_matches_the_kernel_source():
+    """memo.py mirrors compile-time constants of csrc/brta_sweep.cuh (the host cuts slices with them)."""
+    import os
+    import re
+    from basicrta_b200 import memo
+    src = open(os.path.join(os.path.dirname(memo.__file__), 'csrc', 'brta_sweep.cuh')).read()
+    assert int(re.search(r'constexpr int TABLE_FLOATS = (\d+);', src).group(1)) == memo.TABLE_FLOATS
+    assert int(re.search(r'constexpr int PACKED_MAX_ROWS = (\d+);', src).group(1)) == memo.MAX_ROWS
+    assert 'TABLE_FLOATS / table_row_stride(k) < 256' in src and memo.MAX_ROWS == 256
+    # rows = floats / odd row stride, capped: K = 15 -> 240, K = 30 -> 124, K = 2 -> capped at 256
+    assert [memo.table_rows(k) for k in (15, 16, 30, 2)] == [240, 240, 124, 256]
+
+
+def test_gmm_host_packing_and_argument_checks():
+    """Host side of basicrta_b200.gmm (no GPU): parameter blocks, problem packing, sklearn-style errors."""
+    from basicrta_b200 import gmm
+    w = np.array([0.5, 0.3, 0.2])
+    mu = np.arange(6.0).reshape(3, 2)
+    cov = np.array([[[2.0, 0.3], [0.3, 1.0]], [[1.0, 0.0], [0.0, 4.0]], [[0.5, -0.1], [-0.1, 0.7]]])
+    block = gmm.pack_params(w, mu, cov)
+    assert block.shape == (gmm.KMAX, 6) and np.all(block[3:] == 0)
+    w2, mu2, cov2 = gmm._unpack_params(block, 3)
+    assert np.array_equal(w2, w) and np.array_equal(mu2, mu) and np.array_equal(cov2, cov)
+    p = gmm._precisions_cholesky(cov)
+    assert np.allclose(np.einsum('kij,klj->kil', p, p) @ cov, np.eye(2))          # P P^T = cov^-1
+    assert np.all(p[:, 1, 0] == 0)                                                 # upper triangular, like sklearn's
+    flat, offsets, sizes = gmm._pack([np.zeros((5, 2)), np.ones((3, 2))])
+    assert flat.shape == (8, 2) and offsets.tolist() == [0, 5, 8] and sizes.tolist() == [5, 3]
+    with pytest.raises(ValueError):
+        gmm._pack([np.zeros((5, 3))])
+    with pytest.raises(ValueError):
+        gmm.GaussianMixture(n_components=2, init_params='random')
+    assert gmm.fit_batch([], 3, device=0) == []                                    # nothing to do: no GPU touched
