@@ -60,3 +60,22 @@ class ProcessProtein(object):
             f = f'{d}/gibbs_{self.niter}.pkl'
             self.residues[os.path.basename(d)] = f if os.path.exists(f) else None
         return self.residues
+
+    def get_taus(self):
+        """tau of the slowest process of every collected residue and its error bars (cluster.py:97-127); residues
+        without results, or not yet processed, count as ``[0, 0, 0]`` like in the reference."""
+        import numpy as np
+
+        from . import postprocess
+        from .util import get_bars
+        taus = []
+        for res, path in self.residues.items():
+            row = [0, 0, 0]
+            if path is not None:
+                try:
+                    row = postprocess.estimate_tau(Gibbs.load(path))
+                except AttributeError:                                      # no processed_results yet
+                    pass
+            taus.append(row)
+        taus = np.array(taus, dtype=np.float64).reshape(-1, 3)
+        return taus[:, 1], get_bars(taus)

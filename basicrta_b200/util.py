@@ -94,3 +94,9 @@ def run_residue(residue, time, proc, ncomp, niter, cutoff):
     x = np.array(time)
     gib = Gibbs(x, residue, proc, ncomp=ncomp, niter=niter, cutoff=cutoff)
     gib.run()
+
+
+def get_bars(tau):
+    """Error bars (distance of the 95 % bounds from the estimate) of ``[low, tau, high]`` rows: util.py:94-99."""
+    tau = np.asarray(tau, dtype=np.float64)
+    return np.array([tau[:, 1] - tau[:, 0], tau[:, 2] - tau[:, 1]])

@@ -223,6 +223,9 @@ def test_reprocess_fans_every_residue_into_one_batch(tmp_path, monkeypatch):
     pr = loaded.processed_results
     assert pr.ncomp >= 2 and pr.indicator.shape == (2500, pr.ncomp) and len(pr.labels) == len(pr.rates)
     assert pr.parameters.shape == (pr.ncomp, 2) and pr.intervals.shape == (2, pr.ncomp, 2)
+    taus, bars = pp.get_taus()                                               # cluster.py:97-127
+    missing = list(pp.residues).index('D4')
+    assert taus.shape == (4,) and bars.shape == (2, 4) and taus[missing] == 0 and np.all(np.delete(taus, missing) > 0)
     alone = Gibbs.load('basicrta-7.0/A10/gibbs_20000.pkl')
     postprocess.reprocess_batch([alone], device=0, seed=77, save=False)
     assert np.array_equal(alone.processed_results.labels, pr.labels)
