@@ -141,3 +141,20 @@ def test_gmm_host_packing_and_argument_checks():
     with pytest.raises(ValueError):
         gmm.GaussianMixture(n_components=2, init_params='random')
     assert gmm.fit_batch([], 3, device=0) == []                                    # nothing to do: no GPU touched
+
+
+def test_packed_statistics_fields_cannot_overflow():
+    """csrc/brta_sweep.cuh packs (count, sum of tick offsets) of a served datum into one 32-bit atomic: 12 + 20 bits,
+    eight accumulator sets per CTA.  The compile-time limits must keep both fields from overflowing."""
+    import os
+    import re
+    from basicrta_b200 import memo
+    src = open(os.path.join(os.path.dirname(memo.__file__), 'csrc', 'brta_sweep.cuh')).read()
+    max_quads = int(re.search(r'constexpr int PACKED_MAX_QUADS = (\d+);', src).group(1))
+    max_rows = int(re.search(r'constexpr int PACKED_MAX_ROWS = (\d+);', src).group(1))
+    # a set (warp, position in the unrolled pair) sees 128 data per loop iteration of 256 quads, plus one batch of
+    # the single-quad remainder loop
+    per_set = (max_quads // 256 + 1) * 128
+    assert per_set < (1 << 12)
+    assert per_set * (max_rows - 1) < (1 << 20)
+    assert '(1u << 20)' in src and 'w >> 20' in src and '0xfffffu' in src

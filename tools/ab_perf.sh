@@ -1,5 +1,5 @@
 #!/bin/bash
-# developer tool: tools/perf.py for every variants/lib_*.so.  Build a variant with
+# developer tool: tools/perf.py for every variants/lib_*.so (mkdir -p variants first).  Build a variant with
 #   python -c "from basicrta_b200 import _cabi; _cabi.build(force=True, extra_flags=['-DBRTA_SERVED_UNROLL=3'], lib_path='variants/lib_u3.so', ncomps=(15,))"
 for lib in variants/lib_*.so; do
   echo "=== $lib"
