@@ -94,8 +94,9 @@ def test_device_initialisation_equals_its_restatement():
     equal the oracle's restatement (identical discrete decisions; sums in the same order), and so does the
     whole fit."""
     from basicrta_b200 import gmm
-    problems = [cloud(11), cloud(12, 150, FIVE), cloud(13, 50)]
-    ks, ids, seed, n_init = [3, 5, 2], [7, 123456, 99], 2024, 6
+    # incl. the edges: one component, fewer points than threads, as many components as points
+    problems = [cloud(11), cloud(12, 150, FIVE), cloud(13, 50), cloud(14, 43), cloud(15, 9)[:5], cloud(16, 9)[:2]]
+    ks, ids, seed, n_init = [3, 5, 2, 1, 3, 2], [7, 123456, 99, 0, 4294967295, 17], 2024, 6
     fits, raw = gmm.fit_batch(problems, ks, n_init=n_init, seed=seed, problem_ids=ids, return_all=True)
     for p, (x, k) in enumerate(zip(problems, ks)):
         for r in range(n_init):
