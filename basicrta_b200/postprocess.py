@@ -147,7 +147,18 @@ def reprocess_batch(gibbs_list, device=0, n_init=117, seed=None, save=True, pind
     import zlib
 
     from . import gmm
-    inputs = [cluster_inputs(g) for g in gibbs_list]
+    usable, inputs = [], []
+    for g in gibbs_list:                                   # a residue that cannot be clustered fails alone
+        try:
+            inp = cluster_inputs(g)
+            if len(inp[0]) < max(inp[4], 2):               # scikit-learn's "n_samples >= n_components" ValueError
+                raise ValueError('too few retained samples')
+        except (ValueError, IndexError) as err:
+            print(f'{g.residue}: not clustered ({err})')
+            continue
+        usable.append(g)
+        inputs.append(inp)
+    gibbs_list = usable
     ids = [zlib.crc32(f'{g.residue}|{g.cutoff}'.encode()) & 0xFFFFFFFF for g in gibbs_list]
     fits = gmm.fit_batch([np.log(i[0]) for i in inputs], [i[4] for i in inputs], n_init=n_init, seed=seed,
                          device=device, problem_ids=ids)

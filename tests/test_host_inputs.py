@@ -158,3 +158,19 @@ def test_packed_statistics_fields_cannot_overflow():
     assert per_set < (1 << 12)
     assert per_set * (max_rows - 1) < (1 << 20)
     assert '(1u << 20)' in src and 'w >> 20' in src and '0xfffffu' in src
+
+
+def test_reprocess_batch_skips_residues_that_cannot_be_clustered():
+    """cluster.py:44-52: a residue whose clustering raises is skipped, the others go on.  Here every residue is
+    unusable (no samples after burn-in), so nothing reaches the GPU."""
+    import warnings
+    from basicrta_b200 import postprocess
+
+    class Stub(object):
+        pass
+    g = Stub()
+    g.burnin, g.g, g.times, g.residue, g.cutoff = 10000, 100, np.ones(10), 'X1', 7.0
+    g.mcweights, g.mcrates = np.zeros((5, 3)), np.ones((5, 3))
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        assert postprocess.reprocess_batch([g], device=0) == []
