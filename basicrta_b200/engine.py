@@ -455,7 +455,8 @@ class GibbsEngine:
             if shard is not None or flags & (_cabi.FLAG_INJECT_COEF | _cabi.FLAG_INJECT_U | _cabi.FLAG_TRACE):
                 raise ValueError('calibration needs a plain (not sharded, not injected, not traced) batch')
             if choose_kernel is None:
-                choose_kernel = plan.n_waves == 1 and K <= 16 and not flags & (_cabi.FLAG_EXACT | _cabi.FLAG_CTAS3)
+                choose_kernel = (K <= 16 and n_waves is None and not wide and
+                                 not flags & (_cabi.FLAG_EXACT | _cabi.FLAG_CTAS3))
             if choose_kernel:                              # calibrates both candidates itself
                 self._choose_kernel(db, n_data, costs, [int(np.max(ch.ticks)) < 65536 for ch in chains], ticks, tick_offset)
                 plan = db.plan
@@ -523,25 +524,30 @@ class GibbsEngine:
     def _choose_kernel(self, db, n_data, costs, narrow, ticks, tick_offset):
         """K <= 16 comes in two builds: 4 CTAs per SM at 128 registers, and 3 CTAs per SM at 168 registers
         with a third more shared memory per slice (BRTA_FLAG_CTAS3).  Fewer, larger slices mean less
-        per-iteration fixed work per chain, which wins when the batch is small (single-wave schedules:
-        +5-8 % at 50 chains per GPU) and loses when the GPU is full of work.  Rather than guess, time a short
-        launch of each -- after the measured slicing of each -- and keep the faster schedule.  Results do not
-        depend on the choice."""
+        per-iteration fixed work per chain; how that trades against occupancy, and how many waves the 3-CTA
+        build wants, is not something the cost model predicts (C2: 4 CTAs x 2 waves 4.21e12 units/s, 3 CTAs x
+        2 waves 4.06e12, 3 CTAs x 3 waves 4.60e12; 200 residues: 3 CTAs x 2 waves wins; 50-100 residues: 3 CTAs x
+        1 wave).  Rather than guess, time a short launch of each candidate -- the planner's schedule for the
+        4-CTA build, and the 3-CTA build with the same number of waves and, for multi-wave batches, one more --
+        after the measured slicing of each, and keep the fastest.  Results do not depend on the choice."""
         torch = self.torch
         T, H, b = db.tensors, db.host, db.batch
-        for _ in range(CALIBRATE_ROUNDS):
-            self._calibrate(db, costs, ticks, tick_offset)
-        t_base = self._time_short(db, CHOICE_ITERS)
-        base = dict(plan=db.plan, flags=b.flags, tensors={k: T[k] for k in ('tasks', 'cta_task_begin', 'exchange', 'exch_offset')},
-                    host={k: H[k] for k in ('tasks', 'cta_task_begin', 'exch_offset')}, watchdog=b.watchdog_ns)
-        alt_flags = int(b.flags) | _cabi.FLAG_CTAS3
-        try:
-            plan = self._plan(n_data, db.ncomp, alt_flags, costs=costs, narrow=narrow)
-            self._check_slice_sums(plan, ticks, tick_offset, 0, np.asarray(n_data))
-        except (ValueError, _cabi.BrtaError):
-            db.kernel_choice = {'ctas_per_sm': int(base['plan'].grid // self.caps.sm_count), 'ms_4': t_base, 'ms_3': None}
-            return
         dev = T['tasks'].device
+        keys_t = ('tasks', 'cta_task_begin', 'exchange', 'exch_offset')
+        keys_h = ('tasks', 'cta_task_begin', 'exch_offset')
+
+        def snapshot():
+            return dict(plan=db.plan, flags=int(b.flags), tensors={k: T[k] for k in keys_t},
+                        host={k: H[k] for k in keys_h}, watchdog=b.watchdog_ns)
+
+        def restore(snap):
+            T.update(snap['tensors'])
+            H.update(snap['host'])
+            b.flags, b.watchdog_ns = snap['flags'], snap['watchdog']
+            b.tasks, b.cta_task_begin = T['tasks'].data_ptr(), T['cta_task_begin'].data_ptr()
+            b.exchange, b.exch_offset = T['exchange'].data_ptr(), T['exch_offset'].data_ptr()
+            db.plan, db.flags = snap['plan'], int(snap['flags'])
+            b.grid_ctas, b.slice_cap_quads = db.plan.grid, db.plan.smem_units
 
         def up(name, arr):
             pinned = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
@@ -549,32 +555,46 @@ class GibbsEngine:
             T[name] = pinned.to(dev, non_blocking=True)
             return T[name].data_ptr()
 
-        exch_size = np.array([(max(_cabi.exch_bytes(int(c)), 1280) + 127) // 128 * 128 for c in plan.team_size], dtype=np.int64)
-        b.flags = alt_flags
-        b.tasks = up('tasks', plan.tasks.view(np.int32).reshape(-1, 6))
-        b.cta_task_begin = up('cta_task_begin', plan.cta_task_begin)
-        b.exch_offset = up('exch_offset', np.concatenate(([0], np.cumsum(exch_size)[:-1])).astype(np.int64))
-        T['exchange'] = torch.zeros(int(exch_size.sum()), dtype=torch.uint8, device=dev)
-        b.exchange = T['exchange'].data_ptr()
-        b.grid_ctas, b.slice_cap_quads = plan.grid, plan.smem_units
-        b.watchdog_ns = self._watchdog_ns(plan, n_data, db.niter)
-        db.plan, db.flags = plan, alt_flags
-        torch.cuda.current_stream(dev).synchronize()
-        if plan.n_waves == 1:
+        def install(plan, flags):
+            exch_size = np.array([(max(_cabi.exch_bytes(int(c)), 1280) + 127) // 128 * 128 for c in plan.team_size],
+                                 dtype=np.int64)
+            b.flags = flags
+            b.tasks = up('tasks', plan.tasks.view(np.int32).reshape(-1, 6))
+            b.cta_task_begin = up('cta_task_begin', plan.cta_task_begin)
+            b.exch_offset = up('exch_offset', np.concatenate(([0], np.cumsum(exch_size)[:-1])).astype(np.int64))
+            T['exchange'] = torch.zeros(int(exch_size.sum()), dtype=torch.uint8, device=dev)
+            b.exchange = T['exchange'].data_ptr()
+            b.grid_ctas, b.slice_cap_quads = plan.grid, plan.smem_units
+            b.watchdog_ns = self._watchdog_ns(plan, n_data, db.niter)
+            db.plan, db.flags = plan, flags
+            torch.cuda.current_stream(dev).synchronize()
+
+        def measure():
             for _ in range(CALIBRATE_ROUNDS):
                 self._calibrate(db, costs, ticks, tick_offset)
-            t_alt = self._time_short(db, CHOICE_ITERS)
-        else:
-            t_alt = float('inf')
-        db.kernel_choice = {'ms_4': t_base, 'ms_3': t_alt, 'ctas_per_sm': 3 if t_alt < t_base else 4}
-        if t_alt >= t_base:                                          # keep the 4-CTA schedule
-            T.update(base['tensors'])
-            H.update(base['host'])
-            b.flags, b.watchdog_ns = base['flags'], base['watchdog']
-            b.tasks, b.cta_task_begin = T['tasks'].data_ptr(), T['cta_task_begin'].data_ptr()
-            b.exchange, b.exch_offset = T['exchange'].data_ptr(), T['exch_offset'].data_ptr()
-            db.plan, db.flags = base['plan'], int(base['flags'])
-            b.grid_ctas, b.slice_cap_quads = db.plan.grid, db.plan.smem_units
+            return self._time_short(db, CHOICE_ITERS)
+
+        base_waves = int(db.plan.n_waves)
+        tried = [dict(ctas_per_sm=int(db.plan.grid // self.caps.sm_count), n_waves=base_waves, ms=measure())]
+        snaps = [snapshot()]
+        alt_flags = int(b.flags) | _cabi.FLAG_CTAS3
+        for waves in ([base_waves] if base_waves == 1 else [base_waves, base_waves + 1]):
+            try:
+                plan = self._plan(n_data, db.ncomp, alt_flags, n_waves=waves, costs=costs, narrow=narrow)
+                if any(t['ctas_per_sm'] == 3 and t['n_waves'] == plan.n_waves for t in tried):
+                    continue                                 # the wave count was raised to the feasible minimum
+                self._check_slice_sums(plan, ticks, tick_offset, 0, np.asarray(n_data))
+            except (ValueError, _cabi.BrtaError):
+                continue
+            install(plan, alt_flags)
+            tried.append(dict(ctas_per_sm=int(plan.grid // self.caps.sm_count), n_waves=int(plan.n_waves), ms=measure()))
+            snaps.append(snapshot())
+        best = int(np.argmin([t['ms'] for t in tried]))
+        if best != len(tried) - 1:
+            restore(snaps[best])
+        alt = [t['ms'] for t in tried[1:]]
+        db.kernel_choice = {'ctas_per_sm': tried[best]['ctas_per_sm'], 'n_waves': tried[best]['n_waves'],
+                            'ms_4': tried[0]['ms'], 'ms_3': min(alt) if alt else None, 'candidates': tried}
 
     def _measure(self, db, iters):
         """Cycles per task from the start of an iteration to the post of its partials (a short launch

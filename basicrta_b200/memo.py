@@ -37,13 +37,16 @@ class ChainCost:
         if n % 4:
             self.qmax[-1] = np.iinfo(np.int64).max
         self.n_full = n // 4
+        # first quad at or after s that is NOT served by the rows starting at quad s's first tick (the chain is in
+        # ascending-tick order, so qmax is sorted): one vectorised search instead of one per query
+        self._reach = np.searchsorted(self.qmax, self.qmin + self.rows, side='left') if self.rows else None
+        self._splits = {}
 
     def served(self, s, e):
         """Number of quads of slice [s, e) read from the table (a prefix of the slice)."""
         if self.rows == 0 or s >= self.n_full:
             return 0
-        limit = int(self.qmin[s]) + self.rows
-        return int(np.searchsorted(self.qmax[s:e], limit, side='left'))
+        return max(0, min(int(self._reach[s]), e) - s)
 
     def slice_cost(self, s, e):
         k = self.served(s, e)
@@ -67,8 +70,15 @@ class ChainCost:
         return m
 
     def split(self, c, cap=1 << 30):
-        """c + 1 quad boundaries of c slices of (nearly) equal cost, each <= cap quads."""
-        c = int(min(c, self.nq))
+        """c + 1 quad boundaries of c slices of (nearly) equal cost, each <= cap quads.  Memoised: the planner asks
+        for the same (c, cap) when it prices a team size and again when it cuts the slices, and again for every
+        candidate schedule the engine measures."""
+        key = (int(min(c, self.nq)), int(cap))
+        if key not in self._splits:
+            self._splits[key] = self._split(*key)
+        return list(self._splits[key])
+
+    def _split(self, c, cap):
         lo, hi = 0.0, COST_DIRECT * self.nq + 1.0
         for _ in range(40):
             mid = 0.5 * (lo + hi)

@@ -44,7 +44,7 @@ eng = GibbsEngine(0, ctas_per_sm=int(cps) if cps else None, overhead_quads=float
 seg = os.environ.get('BRTA_SEGMENTS')
 db = eng.prepare(chains, 15, niter, thin=100, seed=1, n_waves=int(nw) if nw else None, calibrate=bool(int(os.environ.get('BRTA_CALIBRATE', '0'))),
                  segments=tuple(float(x) for x in seg.split(',')) if seg else None,
-                 flags=_cabi.FLAG_NO_TABLE if 'notable' in sys.argv else 0)
+                 flags=(_cabi.FLAG_NO_TABLE if 'notable' in sys.argv else 0) | int(os.environ.get('BRTA_FLAGS', '0')))
 best = 1e30
 for rep in range(3):
     eng.reset(db)
