@@ -220,7 +220,7 @@ class ClockSampler:
 
 # ---- evidence from the committed ncu captures (profiles/README.md) ---------------------------------
 PROFILE_TRAFFIC = os.path.join(ROOT, 'profiles', 'r2z_dram_bytes_bench.csv')
-PROFILE_FULL = os.path.join(ROOT, 'profiles', 'r2z_ncu_full_selected_c2.csv')
+PROFILE_FULL = os.path.join(ROOT, 'profiles', 'r2y_ncu_full_selected_c2.csv')
 PROFILE_FULL_NITER = 300             # iterations of the launch captured in PROFILE_FULL (tools/perf.py 400 300)
 
 
@@ -623,7 +623,7 @@ def run_b200_arm(args):
                                  'peak.  Data with equal ticks share memoised cumulative rows, so only executed_ex2_share of '
                                  'those ex2 are issued (frac_executed = the XU pipe\'s real load).  The limit the kernel '
                                  'runs into is instruction issue and dependent-instruction latency: issue_frac = executed '
-                                 'warp instructions per unit (ncu, profiles/r2z_ncu_full_selected_c2.csv) x units/s over '
+                                 'warp instructions per unit (ncu, profiles/r2y_ncu_full_selected_c2.csv) x units/s over '
                                  '4 x SMs x clock.',
                          'hbm': {'achieved': algo_bytes / sec / 1e9, 'peak': hbm, 'unit': 'GB/s',
                                  'frac': algo_bytes / sec / 1e9 / hbm,
