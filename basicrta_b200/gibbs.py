@@ -177,6 +177,39 @@ class Gibbs(object):
         with open(savedir + filename, 'w+b') as f:
             dump_reference_pickle(self, f)
 
+    def save_compact(self, path=None):
+        """Opt-in compact side-car of a finished chain: everything ``save`` writes, with the
+        label rows bit-packed (``util.pack_labels``: 4 bits per label for ncomp <= 16 -- half the bytes of the
+        reference pickle, a quarter for ncomp <= 4) in an uncompressed ``.npz``.  The reference pickle stays the
+        default and the only format stock basicrta reads; :meth:`load_compact` restores the same object."""
+        from .util import pack_labels
+        if self.indicator is None:
+            raise ValueError('no label rows on the host (run with keep_indicator_on_device?)')
+        path = path or f'{self._savedir()}/gibbs_{self.niter}.compact.npz'
+        import json
+        scalars = dict(residue=str(self.residue), loc=int(self.loc), ncomp=int(self.ncomp), niter=int(self.niter),
+                       g=int(self.g), burnin=int(self.burnin), noise_cutoff=float(self._noise_cutoff),
+                       cutoff=None if self.cutoff is None else float(self.cutoff))
+        with open(path, 'wb') as f:
+            np.savez(f, packed=pack_labels(self.indicator, self.ncomp), n_data=len(self.times), times=self.times,
+                     mcweights=self.mcweights, mcrates=self.mcrates, t=self.t, s=self.s, whypers=self.whypers,
+                     rhypers=self.rhypers, scalars=np.array(json.dumps(scalars)))
+        return path
+
+    @staticmethod
+    def load_compact(file):
+        """Restore a chain written by :meth:`save_compact` (labels unpacked to the reference's uint8 rows)."""
+        import json
+        from .util import unpack_labels
+        with np.load(file) as z:
+            sc = json.loads(str(z['scalars']))
+            g = Gibbs(z['times'], sc['residue'], sc['loc'], ncomp=sc['ncomp'], niter=sc['niter'], cutoff=sc['cutoff'])
+            g.g, g.burnin, g._noise_cutoff = sc['g'], sc['burnin'], sc['noise_cutoff']
+            g.mcweights, g.mcrates, g.t, g.s = z['mcweights'], z['mcrates'], z['t'], z['s']
+            g.whypers, g.rhypers = z['whypers'], z['rhypers']
+            g.indicator = unpack_labels(z['packed'], g.ncomp, int(z['n_data']))
+        return g
+
     @staticmethod
     def load(file):
         keys = ['times', 'residue', 'loc', 'ncomp', 'niter', 'g', 'burnin',

@@ -100,3 +100,41 @@ def get_bars(tau):
     """Error bars (distance of the 95 % bounds from the estimate) of ``[low, tau, high]`` rows: util.py:94-99."""
     tau = np.asarray(tau, dtype=np.float64)
     return np.array([tau[:, 1] - tau[:, 0], tau[:, 2] - tau[:, 1]])
+
+
+def label_bits(ncomp):
+    """Bits per label of the compact side-car: 1, 2, 4 or 8."""
+    return 1 if ncomp <= 2 else 2 if ncomp <= 4 else 4 if ncomp <= 16 else 8
+
+
+def pack_labels(indicator, ncomp):
+    """uint8 label rows [S, N] -> [S, ceil(N / per)] bytes holding ``per = 8 // label_bits(ncomp)`` labels each,
+    the first label of a group in the low bits (the opt-in compact form of ``indicator``)."""
+    ind = np.ascontiguousarray(indicator, dtype=np.uint8)
+    bits = label_bits(ncomp)
+    if bits == 8:
+        return ind.copy()
+    if ind.size and int(ind.max()) >= (1 << bits):
+        raise ValueError('a label does not fit the bit width of ncomp')
+    per = 8 // bits
+    rows, n = ind.shape
+    padded = np.zeros((rows, -(-n // per) * per), dtype=np.uint8)
+    padded[:, :n] = ind
+    groups = padded.reshape(rows, -1, per)
+    out = np.zeros(groups.shape[:2], dtype=np.uint8)
+    for k in range(per):
+        out |= groups[:, :, k] << np.uint8(bits * k)
+    return out
+
+
+def unpack_labels(packed, ncomp, n_data):
+    """Inverse of :func:`pack_labels`."""
+    packed = np.asarray(packed, dtype=np.uint8)
+    bits = label_bits(ncomp)
+    if bits == 8:
+        return packed[:, :n_data].copy()
+    per = 8 // bits
+    out = np.empty((packed.shape[0], packed.shape[1], per), dtype=np.uint8)
+    for k in range(per):
+        out[:, :, k] = (packed >> np.uint8(bits * k)) & np.uint8((1 << bits) - 1)
+    return out.reshape(packed.shape[0], -1)[:, :n_data].copy()

@@ -247,3 +247,33 @@ def test_compat_shim_exposes_reference_import_paths():
         for k in [k for k in sys.modules if k == 'basicrta' or k.startswith('basicrta.')]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_compact_side_car_round_trips_and_halves_the_labels(tmp_path):
+    """SURVEY.md 8 f-2, second step: the opt-in compact form of a finished chain (bit-packed labels) restores
+    the same object; the reference pickle stays the default."""
+    from basicrta_b200.gibbs import Gibbs
+    from basicrta_b200.util import label_bits, pack_labels, unpack_labels
+    rng = np.random.default_rng(3)
+    for K in (2, 3, 4, 15, 16, 17, 200):
+        for N in (1, 7, 8, 9, 1001):
+            ind = rng.integers(0, K, size=(5, N)).astype(np.uint8)
+            packed = pack_labels(ind, K)
+            assert packed.shape == (5, -(-N * label_bits(K) // 8))
+            assert np.array_equal(unpack_labels(packed, K, N), ind)
+    with pytest.raises(ValueError):
+        pack_labels(np.full((1, 4), 9, np.uint8), 4)
+    times = np.round(rng.exponential(2.0, size=800) / 0.1 + 1) * 0.1
+    g = Gibbs(times, 'W12', 0, ncomp=15, niter=2000, cutoff=7.0)
+    g._prepare(allocate_indicator=False)
+    g.indicator = rng.integers(0, 15, size=(20, 800)).astype(np.uint8)
+    g.mcweights, g.mcrates = rng.random((20, 15)), rng.random((20, 15))
+    path = g.save_compact(str(tmp_path / 'chain.compact.npz'))
+    h = Gibbs.load_compact(path)
+    for name in ('indicator', 'mcweights', 'mcrates', 'times', 't', 's', 'whypers', 'rhypers'):
+        assert np.array_equal(getattr(h, name), getattr(g, name)), name
+    for name in ('residue', 'loc', 'ncomp', 'niter', 'g', 'burnin', 'cutoff', 'ts', '_noise_cutoff'):
+        assert getattr(h, name) == getattr(g, name), name
+    assert h.indicator.dtype == np.uint8
+    with np.load(path) as z:
+        assert z['packed'].nbytes * 2 == g.indicator.nbytes                  # 4 bits per label at K = 15
