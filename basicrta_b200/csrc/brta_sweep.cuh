@@ -16,8 +16,9 @@
 //     registers with the same arithmetic (MUFU.EX2; the oracle's max-subtracted IEEE-only
 //     form in EXACT mode); inverse-CDF label either way (gibbs.py:196-200);
 //   * sufficient statistics (n_k, sum of ticks) are exact integers (gibbs.py:203-207):
-//     shared-memory atomics for every label except the currently dominant one, whose
-//     statistics follow by subtraction from the slice totals;
+//     shared-memory atomics for every label except the one that dominates the CTA's own slice, whose
+//     statistics follow by subtraction from the slice totals; branch-free (a dominant label adds to a
+//     per-lane dummy slot), and in the memoised prefix count and tick offset share ONE 32-bit atomic;
 //   * team members post their partials into the chain's tagged mailboxes in L2 (one
 //     64-bit word per value, valid once it carries the iteration number -- no fence, no
 //     flag) and every warp gathers a share of them; teams wider than 32 CTAs fall back to
