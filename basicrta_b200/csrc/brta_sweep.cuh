@@ -523,7 +523,7 @@ __device__ __forceinline__ void sweep_served(uint32_t slice_addr, int q0, int qb
         }
     const uint32_t dom_off = 4u * (uint32_t)dom;
 #if BRTA_PACKED_STATS
-    static_assert(STRIDE == THREADS && U <= 2, "packed statistics: set = 2 * warp + u");
+    static_assert(STRIDE == THREADS && U <= 2 && WARPS == 4, "packed statistics: eight sets, set = 2 * warp + u");
     const uint32_t stat_base = stat_addr & ~256u;
     const uint32_t dummy = stat_base + 512u + 4u * (threadIdx.x & 31u);
 #if BRTA_PACKED_BY_LANE
